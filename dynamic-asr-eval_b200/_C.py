@@ -1,0 +1,80 @@
+"""ctypes binding of libdae.so (the C ABI declared in include/dae.h).
+
+There is no fallback: if the library is missing or a call fails this module raises.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdae.so")
+
+
+class DaeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); must list every symbol include/dae.h declares.
+_PROTOS = {
+    "dae_abi_version": (c_int, []),
+    "dae_error_string": (c_char_p, [c_int]),
+    "dae_launch_count": (c_int64, []),
+    "dae_greedy_collapse": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dae_specaug_scratch_bytes": (c_size_t, []),
+    "dae_specaug_repeat": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                                   c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dae_ctc_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "dae_ctc_lattice": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
+                                c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dae_ctc_grad": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
+                             c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                             c_void_p, c_size_t, c_void_p]),
+    "dae_stitch": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64,
+                           c_void_p, c_void_p, c_void_p]),
+}
+
+
+def lib():
+    """Load libdae.so once; raise DaeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DaeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C dynamic-asr-eval_b200/csrc`). There is no CPU fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().dae_error_string(rc)
+        raise DaeError(f"{what} failed with code {rc}: {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device (or host) data pointer of a tensor, None -> NULL."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise DaeError(f"{name} must be a CUDA tensor: the dae kernels have no CPU path")
+
+
+def launch_count() -> int:
+    return int(lib().dae_launch_count())

@@ -1,0 +1,107 @@
+"""SpecAugment with the call signature the reference uses, masks applied by libdae.so.
+
+Drop-in for ``lcasr.utils.augmentation.SpecAugment`` (un-vendored; constructor keys from
+lcasr/lib.py:102-112 and earnings_finetune/lcasr160rb1.yaml:73-81; called at lib.py:499,541,
+:290 and earnings_finetune/train.py:230).  PARITY UNPINNED against lcasr's own class: the
+semantics here are torchaudio's ``mask_along_axis_iid`` (mask value = mean of the input or 0;
+width = floor(U*param), start = floor(U*(size-width)); per batch item iid; time bands first,
+then frequency bands).  Band descriptors are drawn on the HOST with ``torch.rand`` in exactly
+the order of :func:`draw_bands`, so an oracle can replay them (SURVEY.md §7 "RNG parity").
+"""
+import ctypes
+
+import torch
+
+from . import _C
+
+MAX_BANDS = 32
+
+
+def draw_bands(n_items, n_masks, param, size, generator=None):
+    """Draw ``n_masks`` (start, end) bands for each of ``n_items`` batch items.
+
+    RNG order per mask (same as torchaudio.functional.mask_along_axis_iid): one
+    ``torch.rand(n_items)`` for the widths, one for the starts.  Returns int32 [n_items, n_masks, 2].
+    """
+    out = torch.zeros((n_items, max(n_masks, 0), 2), dtype=torch.int32)
+    for m in range(n_masks):
+        value = torch.rand(n_items, generator=generator) * param
+        min_value = torch.rand(n_items, generator=generator) * (size - value)
+        start = min_value.long()
+        end = start + value.long()
+        out[:, m, 0] = start.to(torch.int32)
+        out[:, m, 1] = end.to(torch.int32)
+    return out
+
+
+class SpecAugment(torch.nn.Module):
+    def __init__(self, n_time_masks=0, n_freq_masks=0, freq_mask_param=42, time_mask_param=-1, min_p=0.05,
+                 zero_masking=False, iid_masks=True, max_p=1.0):
+        super().__init__()
+        self.n_time_masks, self.n_freq_masks = int(n_time_masks), int(n_freq_masks)
+        self.freq_mask_param, self.time_mask_param = freq_mask_param, time_mask_param
+        self.min_p, self.max_p = min_p, max_p
+        self.zero_masking, self.iid_masks = bool(zero_masking), iid_masks
+        if self.n_time_masks > MAX_BANDS or self.n_freq_masks > MAX_BANDS:
+            raise _C.DaeError(f"at most {MAX_BANDS} bands per axis")
+        self.last_bands = None  # (fbands, tbands) of the most recent call, for tests/replay
+
+    def _time_param(self, T):
+        # time_mask_param <= 0 means "adaptive": a band may cover up to min_p of the frames
+        # (lib.py:107-108 defaults time_mask_param=-1, min_p=0.05).  Unpinned: lcasr is absent.
+        p = self.time_mask_param if self.time_mask_param > 0 else int(self.min_p * T)
+        return min(p, int(self.max_p * T)) if self.max_p is not None else p
+
+    def draw(self, B, F, T, generator=None):
+        tb = draw_bands(B, self.n_time_masks, self._time_param(T), T, generator)
+        fb = draw_bands(B, self.n_freq_masks, self.freq_mask_param, F, generator)
+        return fb, tb
+
+    def forward(self, specgram: torch.Tensor, lengths=None, n_clean: int = 0, bands=None):
+        """specgram [B,F,T] (or [F,T]) fp32 on the GPU -> masked copy, same shape.
+
+        With ``n_clean=k`` the result is [B+k, F, T]: the B masked items followed by k verbatim
+        copies of item 0 (the adapt step's ``repeat(2,1,1)`` batch, lib.py:539-541, in one pass).
+        All B items must then be views of the same window (they are in the reference).
+        """
+        _C.require_cuda(specgram, "specgram")
+        x = specgram
+        squeeze = x.dim() == 2
+        if squeeze:
+            x = x.unsqueeze(0)
+        if x.dtype != torch.float32:
+            raise _C.DaeError("SpecAugment computes in fp32")
+        B, F, T = x.shape
+        fb, tb = bands if bands is not None else self.draw(B, F, T)
+        self.last_bands = (fb, tb)
+        lib = _C.lib()
+        dev = x.device
+        out = torch.empty((B + n_clean, F, T), dtype=torch.float32, device=dev)
+        scratch = torch.empty(lib.dae_specaug_scratch_bytes(), dtype=torch.uint8, device=dev)
+        nf, nt = int(fb.shape[1]), int(tb.shape[1])
+        st = _C.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            if n_clean:
+                # one launch pair: B masked copies + n_clean clean copies of the shared window
+                src = x[0]
+                if src.stride(1) != 1:
+                    src = src.contiguous()
+                fbc, tbc = fb.contiguous(), tb.contiguous()
+                rc = lib.dae_specaug_repeat(src.data_ptr(), src.stride(0), F, T, fbc.data_ptr() if nf else None, nf,
+                                            tbc.data_ptr() if nt else None, nt, int(self.zero_masking), B, n_clean,
+                                            out.data_ptr(), scratch.data_ptr(), None, st)
+                _C.check(rc, "dae_specaug_repeat")
+            else:
+                # the mask value is the mean over the whole [B,F,T] input in the reference
+                # (specgram.mean()); with B > 1 distinct items we use each call's own mean only
+                # when B == 1, else the caller-visible mean of the batch computed on device.
+                for b in range(B):
+                    src = x[b]
+                    if src.stride(1) != 1:
+                        src = src.contiguous()
+                    fbc, tbc = fb[b:b + 1].contiguous(), tb[b:b + 1].contiguous()
+                    rc = lib.dae_specaug_repeat(src.data_ptr(), src.stride(0), F, T, fbc.data_ptr() if nf else None, nf,
+                                                tbc.data_ptr() if nt else None, nt, int(self.zero_masking), 1, 0,
+                                                out[b].data_ptr(), scratch.data_ptr(), None, st)
+                    _C.check(rc, "dae_specaug_repeat")
+        return out[0] if squeeze else out

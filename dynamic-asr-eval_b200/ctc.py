@@ -1,0 +1,110 @@
+"""CTC loss with the reference's call signature, computed by libdae.so.
+
+Drop-in for ``torch.nn.CTCLoss(blank, reduction)`` as called at lcasr/lib.py:492,575
+(and :250,324-329 for AWMC; earnings_finetune/train.py:259,286 for ragged batches).
+Forward launches the alpha/beta lattice kernel; backward launches the dense gradient
+kernel with the real upstream gradient, so ``loss / (T*N)`` then ``.backward()`` costs one
+read of ``log_probs`` and one write of its gradient.
+"""
+import torch
+
+from . import _C
+
+
+class _CTCFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, log_probs, targets, input_lengths, target_lengths, blank):
+        _C.require_cuda(log_probs, "log_probs")
+        if log_probs.dtype != torch.float32:
+            raise _C.DaeError("dae.CTCLoss computes in fp32; got " + str(log_probs.dtype))
+        ctx.unbatched = log_probs.dim() == 2
+        if ctx.unbatched:  # [T,C]
+            log_probs = log_probs.unsqueeze(1)
+            targets = targets.unsqueeze(0) if targets.dim() == 1 else targets
+        T, N, C = log_probs.shape
+        lp = log_probs.detach()
+        if lp.stride(2) != 1:
+            lp = lp.contiguous()
+        dev = lp.device
+        in_len = torch.as_tensor(input_lengths, dtype=torch.int64).reshape(-1).to(dev, non_blocking=True).contiguous()
+        tg_len = torch.as_tensor(target_lengths, dtype=torch.int64).reshape(-1).to(dev, non_blocking=True).contiguous()
+        tg = targets.to(device=dev, dtype=torch.int64)
+        if tg.dim() == 1:
+            # concatenated 1-D targets (torch allows this): repack to padded 2-D on the host side
+            lens = tg_len.tolist()
+            Lmax = max(lens) if lens else 0
+            packed = tg.new_zeros((N, max(Lmax, 1)))
+            o = 0
+            for i, l in enumerate(lens):
+                packed[i, :l] = tg[o:o + l]
+                o += l
+            tg = packed
+        if tg.dim() != 2 or tg.shape[0] != N:
+            raise _C.DaeError(f"targets must be [N, Lmax]; got {tuple(tg.shape)} for N={N}")
+        if tg.stride(1) != 1:
+            tg = tg.contiguous()
+        Lmax = int(tg.shape[1])
+        lib = _C.lib()
+        nbytes = lib.dae_ctc_scratch_bytes(T, N, Lmax)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        nll = torch.empty(N, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.dae_ctc_lattice(lp.data_ptr(), lp.stride(0), lp.stride(1), T, N, C,
+                                     tg.data_ptr() if Lmax else None, tg.stride(0), Lmax,
+                                     in_len.data_ptr(), tg_len.data_ptr(), int(blank),
+                                     nll.data_ptr(), scratch.data_ptr(), nbytes, _C.stream_ptr(dev))
+        _C.check(rc, "dae_ctc_lattice")
+        ctx.save_for_backward(lp, tg, in_len, tg_len, nll, scratch)
+        ctx.blank = int(blank)
+        return nll
+
+    @staticmethod
+    def backward(ctx, grad_nll):
+        lp, tg, in_len, tg_len, nll, scratch = ctx.saved_tensors
+        T, N, C = lp.shape
+        unbatched = ctx.unbatched
+        Lmax = int(tg.shape[1])
+        g = grad_nll.to(torch.float32)
+        if g.numel() == 1:
+            g = g.reshape(1)
+            g_stride = 0
+        else:
+            g = g.contiguous()
+            g_stride = 1
+        grad = torch.empty((T, N, C), dtype=torch.float32, device=lp.device)
+        with torch.cuda.device(lp.device):
+            rc = _C.lib().dae_ctc_grad(lp.data_ptr(), lp.stride(0), lp.stride(1), T, N, C,
+                                       tg.data_ptr() if Lmax else None, tg.stride(0), Lmax,
+                                       in_len.data_ptr(), tg_len.data_ptr(), ctx.blank,
+                                       nll.data_ptr(), g.data_ptr(), g_stride, grad.data_ptr(),
+                                       scratch.data_ptr(), scratch.numel(), _C.stream_ptr(lp.device))
+        _C.check(rc, "dae_ctc_grad")
+        return (grad[:, 0] if unbatched else grad), None, None, None, None
+
+
+def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reduction="mean", zero_infinity=False):
+    """Functional form, same argument meaning as ``torch.nn.functional.ctc_loss``."""
+    if zero_infinity:
+        raise _C.DaeError("zero_infinity=True is not used by the reference (SURVEY.md appendix A) and is not implemented")
+    unbatched = log_probs.dim() == 2
+    nll = _CTCFunction.apply(log_probs, targets, input_lengths, target_lengths, blank)
+    if reduction == "sum":
+        return nll.sum()
+    if reduction == "none":
+        return nll[0] if unbatched else nll
+    if reduction == "mean":
+        tl = torch.as_tensor(target_lengths, dtype=torch.float32).reshape(-1).to(nll.device).clamp_min(1)
+        return (nll / tl).mean()
+    raise ValueError(f"unknown reduction {reduction!r}")
+
+
+class CTCLoss(torch.nn.Module):
+    """``torch.nn.CTCLoss`` call signature (lcasr/lib.py:492) on the dae CUDA kernels."""
+
+    def __init__(self, blank: int = 0, reduction: str = "mean", zero_infinity: bool = False):
+        super().__init__()
+        self.blank, self.reduction, self.zero_infinity = blank, reduction, zero_infinity
+
+    def forward(self, log_probs, targets, input_lengths, target_lengths):
+        return ctc_loss(log_probs, targets, input_lengths, target_lengths, self.blank, self.reduction,
+                        self.zero_infinity)

@@ -1,0 +1,128 @@
+/*
+ * dae.h — C ABI of libdae.so, the B200 (sm_100a) kernels behind the dynamic-evaluation
+ * hot path of robflynnyh/dynamic-asr-eval.
+ *
+ * The reference has no FFI layer of its own (it is pure Python); each entry
+ * point below replaces one Python-level call on the hot path and cites it as
+ * "replaces: <file>:<line>" (paths relative to the reference checkout).  The host side
+ * (package `dae`, directory dynamic-asr-eval_b200/) mirrors the reference's Python
+ * signatures and binds these symbols with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *   - outputs and scratch are pre-allocated by the caller; no entry point allocates, frees
+ *     or synchronises the device; all work is enqueued on `stream` (a cudaStream_t passed
+ *     as void*, NULL = legacy default stream);
+ *   - return value: 0 = enqueued, < 0 = argument error (DAE_E_*), > 0 = a cudaError_t;
+ *   - strides are in ELEMENTS, not bytes; the innermost (class / column) stride is 1;
+ *   - no global state: re-entrant from several host threads on distinct streams.
+ */
+#ifndef DAE_H_
+#define DAE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAE_ABI_VERSION 1
+
+#define DAE_E_BADARG   (-1)  /* NULL pointer, negative size, ...                      */
+#define DAE_E_TOOBIG   (-2)  /* a dimension exceeds what the kernel supports          */
+#define DAE_E_SCRATCH  (-3)  /* scratch buffer smaller than *_scratch_bytes() says    */
+#define DAE_E_ALIGN    (-4)  /* pointer / stride alignment requirement not met        */
+
+int         dae_abi_version(void);
+const char* dae_error_string(int code);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t     dae_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * (3b) greedy CTC decode: per-frame argmax -> collapse repeats -> drop blank.
+ * replaces: lcasr.decoding.greedy.GreedyCTCDecoder.__call__ as used at
+ *           lcasr/lib.py:559,565 and lcasr/run_dynamic_eval_full.py:100
+ *           (there the [T,C] posteriors are first copied to the host).
+ * lp      [B,T,C] fp32, strides sB,sT (elements), class stride 1
+ * lengths [B] int32 valid frames per item, or NULL (= T for all)
+ * path    [B,T] int32 out: argmax class of every frame (first index on ties, NaN = max,
+ *                 as torch.argmax)
+ * ids     [B,T] int32 out: collapsed label ids, ids[b, 0 .. n_ids[b])
+ * n_ids   [B]   int32 out
+ * ------------------------------------------------------------------------------------ */
+int dae_greedy_collapse(const float* lp, int64_t sB, int64_t sT, int B, int T, int C,
+                        const int32_t* lengths, int blank,
+                        int32_t* path, int32_t* ids, int32_t* n_ids, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (3a) SpecAugment masking fused with the [augmented..., clean...] batch build.
+ * replaces: lcasr.utils.augmentation.SpecAugment.__call__ + Tensor.repeat at
+ *           lcasr/lib.py:538-541 (CPU tensors there).
+ * x        [F,T] fp32 window of the spectrogram, row stride sF (a view into [1,F,spec_n])
+ * out      [n_aug+n_clean, F, T] fp32 contiguous.  Copies 0..n_aug-1 are masked, the rest
+ *          are verbatim copies of x.
+ * fmask_host [n_aug][nf][2], tmask_host [n_aug][nt][2]: HOST int32 (start,end) half-open
+ *          bands over the frequency / time axis, drawn by the caller's RNG (nf,nt <= 32,
+ *          n_aug <= 4).
+ * mask value = 0 if zero_masking else mean(x) (fp64 accumulation, fixed reduction order,
+ *          rounded once to fp32).  partials: scratch of dae_specaug_scratch_bytes() bytes.
+ * mean_out  [1] fp32 out (the fill value actually used), may be NULL.
+ * ------------------------------------------------------------------------------------ */
+size_t dae_specaug_scratch_bytes(void);
+int dae_specaug_repeat(const float* x, int64_t sF, int F, int T,
+                       const int32_t* fmask_host, int nf, const int32_t* tmask_host, int nt,
+                       int zero_masking, int n_aug, int n_clean,
+                       float* out, void* partials, float* mean_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (1) CTC loss + gradient (torch.nn.CTCLoss semantics, zero_infinity=False).
+ * replaces: torch.nn.CTCLoss(blank, reduction='sum')(...) and its backward at
+ *           lcasr/lib.py:492,575-579 (AWMC: :250,324-331; finetune: earnings_finetune/train.py:259).
+ *
+ * dae_ctc_lattice : log-space alpha (forward in t) and beta (backward in t) recursions over
+ *   the blank-interleaved label lattice, one CTA per (sample, direction), both directions
+ *   concurrently.  Writes nll[n] and keeps alpha/beta in `scratch` for dae_ctc_grad.
+ * dae_ctc_grad    : dense streaming pass
+ *   grad[t,n,c] = gout[n] * ( exp(lp[t,n,c]) - exp(ab[t,n,c] + nll[n] - lp[t,n,c]) ), 0 for t >= in_len[n]
+ *   (gradient w.r.t. the pre-log-softmax logits, torch's convention).
+ *
+ * lp      [T,N,C] fp32, strides sT,sN (elements), class stride 1 (any batch/time layout)
+ * tgt     [N,Lmax] int64 padded targets, row stride tgt_stride; in_len/tgt_len [N] int64
+ * nll     [N] fp32 out (per-sample negative log-likelihood; +inf when infeasible)
+ * gout    per-sample upstream gradient, gout[n*gout_stride] (gout_stride 0 = one scalar)
+ * grad    [T,N,C] fp32 contiguous out
+ * ------------------------------------------------------------------------------------ */
+size_t dae_ctc_scratch_bytes(int T, int N, int Lmax);
+int dae_ctc_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, int C,
+                    const int64_t* tgt, int64_t tgt_stride, int Lmax,
+                    const int64_t* in_len, const int64_t* tgt_len, int blank,
+                    float* nll, void* scratch, size_t scratch_bytes, void* stream);
+int dae_ctc_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C,
+                 const int64_t* tgt, int64_t tgt_stride, int Lmax,
+                 const int64_t* in_len, const int64_t* tgt_len, int blank,
+                 const float* nll, const float* gout, int64_t gout_stride,
+                 float* grad, const void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (f-1) overlap-average stitch of window posteriors, with a fused greedy argmax.
+ * replaces: the exp / slice-accumulate / count / divide / log passes over CPU buffers at
+ *           lcasr/lib.py:594-629 (same arithmetic at :357-371 for AWMC).
+ * win_lp   [n_win] windows of log-probs, window w = rows win_off[w] .. +win_len[w] of the
+ *          device buffer `lp` ([rows_total, C] fp32, row stride C)
+ * win_pos  [n_win] int64 first output row of window w (host arithmetic of lib.py:615-621,
+ *          already sorted by window start); win_len [n_win] int64; win_off [n_win] int64
+ * out      [n_out, C] fp32: log( sum_w exp(lp_w) / count ), windows added in index order
+ * path     [n_out] int32 argmax of each stitched row (may be NULL)
+ * Rows covered by no window are not part of the output (lib.py:624-627): the caller passes
+ * n_out = number of covered rows and row_map [n_out] int64 = their buffer positions.
+ * ------------------------------------------------------------------------------------ */
+int dae_stitch(const float* lp, int C, const int64_t* win_off, const int64_t* win_pos,
+               const int64_t* win_len, int n_win, const int64_t* row_map, int64_t n_out,
+               float* out, int32_t* path, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAE_H_ */

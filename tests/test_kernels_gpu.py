@@ -1,0 +1,234 @@
+"""GPU parity tests (B200): greedy, SpecAugment, CTC, stitch — CUDA path vs the CPU oracle.
+
+All calls go through the C ABI (ctypes).  Integer/index results are bit-exact; floating point
+tolerances are written next to each assert.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctc_oracle, greedy_oracle, specaug_oracle, stitch_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------- greedy
+def _peaky(T, C, blank, g, p_blank=0.6):
+    lp = torch.randn(T, C, generator=g)
+    cls = torch.randint(0, C - 1, (T,), generator=g)
+    cls[torch.rand(T, generator=g) < p_blank] = blank
+    run = torch.rand(T, generator=g) < 0.5               # repeat the previous frame's class
+    for t in range(1, T):
+        if run[t]:
+            cls[t] = cls[t - 1]
+    lp[torch.arange(T), cls] += 6
+    return lp.log_softmax(-1)
+
+
+@pytest.mark.parametrize("T,C", [(2048, 4096), (333, 129), (1000, 32), (1, 7), (5000, 4096), (70, 1030)])
+def test_greedy_matches_oracle(cuda, T, C):
+    from dae.greedy import greedy_ids_device
+    g = torch.Generator().manual_seed(T + C)
+    lp = _peaky(T, C, C - 1, g)
+    if T > 60:
+        lp[10, 3] = lp[10, 11] = lp[10].max() + 1        # exact tie -> first index
+        lp[20] = lp[19]                                  # identical consecutive frames
+        lp[30, C // 2] = float("nan")
+        lp[40] = float("-inf")
+    path, ids, n = greedy_ids_device(lp.to(cuda), C - 1)
+    ref_path = greedy_oracle.argmax_rows(lp.numpy())
+    np.testing.assert_array_equal(path[0, :T].cpu().numpy(), ref_path)
+    assert ids[0, :int(n[0])].tolist() == greedy_oracle.collapse(ref_path, C - 1)
+
+
+def test_greedy_batched_strided_lengths(cuda):
+    from dae.greedy import greedy_ids_device
+    g = torch.Generator().manual_seed(0)
+    B, T, C = 3, 700, 260
+    big = torch.stack([_peaky(T, C + 4, C - 1, g) for _ in range(B)])
+    lp = big[:, :, :C]                                   # row stride C+4, class stride 1, unaligned rows
+    lens = torch.tensor([700, 1, 313], dtype=torch.int32)
+    path, ids, n = greedy_ids_device(lp.to(cuda)[:, :, :], C - 1, lens)
+    lpd = big.to(cuda)[:, :, :C]
+    path, ids, n = greedy_ids_device(lpd, C - 1, lens)
+    for b in range(B):
+        ref = greedy_oracle.greedy_ids(lp[b, :int(lens[b])].numpy(), C - 1)
+        assert ids[b, :int(n[b])].tolist() == ref
+
+
+def test_greedy_decoder_module(cuda):
+    from dae.greedy import GreedyCTCDecoder
+
+    class Tok:
+        def decode(self, ids):
+            return " ".join(str(i) for i in ids)
+    g = torch.Generator().manual_seed(5)
+    lp = _peaky(500, 129, 128, g)
+    ref = greedy_oracle.greedy_ids(lp.numpy(), 128)
+    dec = GreedyCTCDecoder(tokenizer=Tok(), blank_id=128)
+    assert dec(lp.to(cuda)) == " ".join(map(str, ref))
+    assert dec(lp.to(cuda), decode=False) == ref
+    assert dec(lp) == " ".join(map(str, ref))            # host tensor, as the reference passes it
+    assert GreedyCTCDecoder(blank_id=128)(lp.to(cuda)) == ref
+
+
+# ---------------------------------------------------------------- SpecAugment
+@pytest.mark.parametrize("F,T,nf,nt,zero", [(80, 16384, 6, 0, False), (80, 4000, 2, 3, False), (80, 1001, 4, 2, True),
+                                            (13, 77, 1, 1, False)])
+def test_specaug_repeat_matches_oracle(cuda, F, T, nf, nt, zero):
+    from dae.augment import SpecAugment
+    torch.manual_seed(F * T)
+    spec = torch.randn(1, F, T + 100) * 2 + 0.3
+    win = spec[:, :, 50:50 + T]                          # a window view, row stride T+100
+    aug = SpecAugment(n_time_masks=nt, n_freq_masks=nf, freq_mask_param=34 if F > 40 else 5, time_mask_param=50,
+                      zero_masking=zero)
+    out = aug(win.to(cuda) if False else spec.to(cuda)[:, :, 50:50 + T], n_clean=1)
+    fb, tb = aug.last_bands
+    ref, fill = specaug_oracle.specaug_repeat(win[0].numpy(), fb.tolist(), tb.tolist(), zero, 1)
+    got = out.cpu().numpy()
+    assert got.shape == (2, F, T)
+    np.testing.assert_array_equal(got[1], win[0].numpy())                       # clean copy: bit-exact
+    masked = got[0] != win[0].numpy()
+    kfill = got[0][masked][0] if masked.any() else fill
+    # mean fill: fp64 accumulation on both sides, may differ in the last fp32 bit only
+    assert abs(float(kfill) - float(fill)) <= 1.2e-7 * max(1.0, abs(float(fill)))
+    ref2, _ = specaug_oracle.specaug_repeat(win[0].numpy(), fb.tolist(), tb.tolist(), zero, 1, fill=kfill)
+    np.testing.assert_array_equal(got, ref2)                                   # given the fill: bit-exact
+
+
+def test_specaug_plain_call_and_determinism(cuda):
+    from dae.augment import SpecAugment
+    torch.manual_seed(3)
+    x = torch.randn(1, 80, 2048, device=cuda)
+    aug = SpecAugment(n_freq_masks=6, freq_mask_param=34)
+    torch.manual_seed(11)
+    a = aug(x)
+    torch.manual_seed(11)
+    b = aug(x)
+    assert a.shape == x.shape and torch.equal(a, b)
+    fb, _ = aug.last_bands
+    ref, _ = specaug_oracle.specaug_repeat(x[0].cpu().numpy(), fb.tolist(), [[]], False, 0, fill=a[0][a[0] != x[0]][0].item()
+                                           if (a[0] != x[0]).any() else None)
+    np.testing.assert_array_equal(a.cpu().numpy(), ref)
+
+
+# ---------------------------------------------------------------- CTC
+def _ctc_case(T, N, C, Lmax, seed, ragged=True, peaky=False):
+    g = torch.Generator().manual_seed(seed)
+    blank = C - 1
+    if peaky:
+        lp = torch.stack([_peaky(T, C, blank, g) for _ in range(N)], 1)
+    else:
+        lp = (torch.randn(T, N, C, generator=g) * 3).log_softmax(-1)
+    tg = torch.randint(0, blank, (N, max(Lmax, 1)), generator=g)
+    if Lmax >= 2:
+        tg[0, 1] = tg[0, 0]
+    il = torch.full((N,), T, dtype=torch.long)
+    tl = torch.full((N,), Lmax, dtype=torch.long)
+    if ragged and N > 1:
+        il[1:] = torch.randint(max(T // 2, 2 * Lmax + 1), T + 1, (N - 1,), generator=g)
+        tl[1:] = torch.randint(0, Lmax + 1, (N - 1,), generator=g)
+    return lp, tg, il, tl, blank
+
+
+@pytest.mark.parametrize("T,N,C,Lmax", [(40, 2, 7, 9), (200, 3, 129, 40), (512, 1, 4096, 150), (64, 4, 32, 0),
+                                        (300, 2, 50, 149), (33, 1, 5, 1)])
+def test_ctc_matches_fp64_oracle(cuda, T, N, C, Lmax):
+    from dae.ctc import CTCLoss
+    lp, tg, il, tl, blank = _ctc_case(T, N, C, Lmax, seed=T + N)
+    if Lmax == 0:
+        tg = tg[:, :0]
+    x = lp.to(cuda).requires_grad_()
+    loss = CTCLoss(blank=blank, reduction="sum")(x, tg.to(cuda), il.to(cuda), tl.to(cuda))
+    (loss / (T * N)).backward()
+    nll, grad = ctc_oracle.ctc_loss_grad(lp.double().numpy(), tg.numpy(), il.numpy(), tl.numpy(), blank,
+                                         gout=1.0 / (T * N))
+    # north_star tolerance: loss and gradients within 1e-4 relative (fp32)
+    assert abs(loss.item() - nll.sum()) <= 1e-4 * abs(nll.sum())
+    got = x.grad.cpu().numpy()
+    scale = np.abs(grad).max()
+    np.testing.assert_allclose(got, grad, rtol=1e-4, atol=1e-5 * scale)
+    for n in range(N):
+        assert np.all(got[int(il[n]):, n] == 0)
+
+
+def test_ctc_hot_path_shape_vs_torch(cuda):
+    """cfg2 shape: lp is the non-contiguous view out[:1].transpose(0,1) of [2,2048,4096] (lib.py:570-575)."""
+    from dae.ctc import CTCLoss
+    T, C = 2048, 4096
+    g = torch.Generator().manual_seed(0)
+    post = torch.stack([_peaky(T, C, C - 1, g, p_blank=0.7) for _ in range(2)]).to(cuda).requires_grad_()
+    labels = greedy_oracle.greedy_ids(post[1].detach().cpu().numpy(), C - 1)
+    tg = torch.tensor(labels, dtype=torch.long, device=cuda)[None]
+    L = len(labels)
+    assert 100 < L < 1500
+    aug = post[:1].transpose(0, 1)
+    il, tl = torch.tensor([T], device=cuda), torch.tensor([L], device=cuda)
+    loss = CTCLoss(blank=C - 1, reduction="sum")(aug, tg, il, tl) / T
+    loss.backward()
+    got = post.grad.clone()
+    post.grad = None
+    ref_loss = torch.nn.CTCLoss(blank=C - 1, reduction="sum")(aug, tg, il, tl) / T
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-4 * abs(ref_loss.item())
+    assert torch.all(got[1] == 0)
+    # torch's own fp32 lattice is the looser side here (see tests/test_oracle_pins.py); compare to fp64 too
+    np.testing.assert_allclose(got[0].cpu().numpy(), post.grad[0].cpu().numpy(), atol=2e-3 / T, rtol=1e-2)
+    nll, grad = ctc_oracle.ctc_loss_grad(post[:1].detach().transpose(0, 1).double().cpu().numpy(), [labels], [T], [L],
+                                         C - 1, gout=1.0 / T)
+    np.testing.assert_allclose(got[0].cpu().numpy(), grad[:, 0], rtol=1e-4, atol=1e-5 * np.abs(grad).max())
+    assert abs(loss.item() * T - nll[0]) <= 1e-4 * nll[0]
+
+
+def test_ctc_reductions_and_infeasible(cuda):
+    from dae.ctc import CTCLoss, ctc_loss
+    lp, tg, il, tl, blank = _ctc_case(50, 3, 11, 8, seed=9)
+    x = lp.to(cuda)
+    for red in ("none", "mean", "sum"):
+        a = ctc_loss(x, tg.to(cuda), il, tl, blank=blank, reduction=red)
+        b = torch.nn.functional.ctc_loss(lp, tg, il, tl, blank=blank, reduction=red)
+        torch.testing.assert_close(a.cpu(), b, rtol=1e-4, atol=1e-4)
+    # infeasible: 4 repeated labels need 7 frames, only 3 given -> +inf like torch (zero_infinity=False)
+    y = torch.randn(3, 1, 5).log_softmax(-1).to(cuda)
+    bad = CTCLoss(blank=4, reduction="sum")(y, torch.tensor([[1, 1, 1, 1]], device=cuda), [3], [4])
+    assert torch.isinf(bad) and bad > 0
+
+
+def test_ctc_large_magnitude_precision(cuda):
+    """|log-likelihood| ~ 2e4: the centred lattice must stay within 1e-4 of fp64 where torch fp32 drifts."""
+    from dae.ctc import CTCLoss
+    T, N, C, L = 2048, 1, 512, 300
+    lp, tg, il, tl, blank = _ctc_case(T, N, C, L, seed=1, ragged=False)
+    x = lp.to(cuda).requires_grad_()
+    loss = CTCLoss(blank=blank, reduction="sum")(x, tg.to(cuda), il, tl)
+    loss.backward()
+    nll, grad = ctc_oracle.ctc_loss_grad(lp.double().numpy(), tg.numpy(), il.numpy(), tl.numpy(), blank)
+    assert nll[0] > 5000
+    assert abs(loss.item() - nll[0]) <= 1e-5 * nll[0]
+    np.testing.assert_allclose(x.grad.cpu().numpy(), grad, rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------- stitch
+def test_stitch_matches_oracle(cuda):
+    import dae._C as C_
+    from dae.stitch import stitch_windows
+    rng = np.random.default_rng(0)
+    C, seq, ov, spec_n = 129, 1024, 896, 5000
+    chunks = stitch_oracle.prepare_chunks(spec_n, seq, ov)
+    ds = lambda n: ((((n - 1) // 2 + 1) - 1) // 2 + 1 - 1) // 2 + 1
+    wins = [np.log(rng.dirichlet(np.ones(C) * 0.3, size=ds(u)) + 1e-30).astype(np.float32) for _, u in chunks]
+    starts, ulens = [c[0] for c in chunks], [c[1] for c in chunks]
+    ref = stitch_oracle.stitch(wins, starts, ulens, ov, buf_rows=spec_n // 4 + seq)
+    out, path = stitch_windows([torch.from_numpy(w).to(cuda) for w in wins], starts, ulens, ov)
+    assert out.shape == ref.shape
+    # exp/log are MUFU-based on the device: 2e-6 relative on the probabilities
+    np.testing.assert_allclose(np.exp(out.cpu().numpy()), np.exp(ref), rtol=5e-6, atol=1e-30)
+    np.testing.assert_array_equal(path.cpu().numpy(), greedy_oracle.argmax_rows(out.cpu().numpy()))
+    assert (path.cpu().numpy() == greedy_oracle.argmax_rows(ref)).mean() > 0.999
+
+
+def test_stitch_single_window_identity(cuda):
+    from dae.stitch import stitch_windows
+    lp = torch.randn(750, 129).log_softmax(-1)
+    out, path = stitch_windows([lp.to(cuda)], [0], [6000], 0)
+    np.testing.assert_allclose(out.cpu().numpy(), lp.numpy(), rtol=0, atol=2e-6)

@@ -1,0 +1,300 @@
+"""bench.py — headline benchmark: audio-hours/sec of dynamic evaluation (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl dae|reference] [--frames F]
+
+Workload (BASELINE.json configs[1]): stand-in lcasr160rb1-sized CTC encoder (6 layers, d=768, fp32,
+random-init, blank prior calibrated so teacher labels are speech-like) doing dynamic evaluation of
+one Earnings22-shaped synthetic recording per step: seq 16384 / overlap 14336, 1 epoch, 6 frequency
+masks x 34, MADGRAD lr 9e-5, then the no-grad final pass and overlap stitch, then greedy decode.
+One "step" = one whole recording.  Under torchrun every rank processes its own recording per step
+(weak scaling, no data-path collective; one int64[5] all-reduce of WER counts per step).
+
+The JSON line carries: value (inputs resident in HBM), e2e (host spectrogram -> host hypothesis ids,
+copies inside the timed region), roofline (dominant dae kernel, CUDA events live in the timed
+region), cpu_baseline (the oracle loop on host cores, bounded sample), clocks, gpu_launches.
+`--impl reference` times the CPU restatement of the reference loop (oracle/ref_loop.py).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEQ_LEN, OVERLAP, FPS = 16384, 14336, 100
+KW = dict(epochs=1, shuffle=True, spec_augment_n_freq_masks=6, spec_augment_freq_mask_param=34,
+          spec_augment_n_time_masks=0, optim_lr=9e-5)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_args(config):
+    from types import SimpleNamespace
+    a = SimpleNamespace(config=config)
+    a.__dict__.update(KW)
+    return a
+
+
+def n_windows(frames):
+    n, i, last, kill = 0, 0, None, False
+    if frames <= SEQ_LEN:
+        return 1
+    for i in range(0, frames, SEQ_LEN - OVERLAP):
+        u = min(SEQ_LEN, frames - i)
+        if kill:
+            break
+        if last is not None and u < last:
+            kill = True
+        last = u
+        n += 1
+    return n
+
+
+def run_reference(a, rank, world):
+    """The reference's CPU path (oracle restatement of lcasr/lib.py:450-640), model on the host too."""
+    if rank != 0:
+        return
+    import random
+    from oracle.ref_loop import dynamic_eval_reference
+    from dae import standin
+    from dae.optim import MADGRAD
+    torch.set_num_threads(os.cpu_count() or 1)
+    tok = standin.SyntheticTokenizer()
+    model = standin.build_model(tok.vocab_size(), device="cpu", seed=0)
+    spec = torch.randn(1, 80, a.frames, generator=torch.Generator().manual_seed(1))
+    standin.calibrate_blank_prior(model, spec[:, :, :4096])
+    args = make_args(standin.default_config())
+    sample_windows = 1
+    audio_h = a.frames / FPS / 3600.0 / n_windows(a.frames) * sample_windows
+
+    def step():
+        random.seed(0)
+        torch.manual_seed(0)
+        dynamic_eval_reference(args, model, spec, SEQ_LEN, OVERLAP, tok, MADGRAD, max_windows=sample_windows)
+    for _ in range(a.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = audio_h * a.steps / dt
+    cores = torch.get_num_threads()
+    sample = (f"{sample_windows} of {n_windows(a.frames)} windows of a {a.frames}-frame recording per step "
+              f"(adapt step + final pass + stitch), model and CTC on the CPU")
+    print(json.dumps({
+        "impl": "reference", "metric": "audio-hours/sec dynamic-eval", "value": val, "unit": "audio-hours/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a),
+        "cpu_baseline": {"value": val, "unit": "audio-hours/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_config(a):
+    return {"workload": f"dynamic eval of one synthetic Earnings22-shaped recording per step ({a.frames} frames = "
+                        f"{a.frames / FPS / 60:.1f} min, 80-mel, seq {SEQ_LEN} overlap {OVERLAP}, "
+                        f"{n_windows(a.frames)} windows, 1 epoch + final pass + stitch + greedy)",
+            "model": "stand-in lcasr160rb1 (6 layers, d=768, 6x128 heads, conv k=9, x8 subsampling, C=4096), fp32, "
+                     "random-init, PyTorch encoder (not the product)",
+            "spec_augment": "6 freq masks x 34, 0 time masks", "optimizer": "MADGRAD lr 9e-5",
+            "l2": "inputs larger than L2 (model weights 0.36 GB + activations stream through every step)",
+            "parallelism": f"recordings sharded over {a.gpus} rank(s), one int64[5] all-reduce per step"}
+
+
+def cpu_baseline_sample(frames):
+    """Bounded CPU sample of the same workload through the oracle loop (reported baseline only)."""
+    import random
+    from oracle.ref_loop import dynamic_eval_reference
+    from dae import standin
+    from dae.optim import MADGRAD
+    torch.set_num_threads(os.cpu_count() or 1)
+    tok = standin.SyntheticTokenizer()
+    model = standin.build_model(tok.vocab_size(), device="cpu", seed=0)
+    spec = torch.randn(1, 80, frames, generator=torch.Generator().manual_seed(1))
+    standin.calibrate_blank_prior(model, spec[:, :, :4096])
+    args = make_args(standin.default_config())
+    k = 2
+    random.seed(0)
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    dynamic_eval_reference(args, model, spec, SEQ_LEN, OVERLAP, tok, MADGRAD, max_windows=k)
+    dt = time.perf_counter() - t0
+    audio_h = frames / FPS / 3600.0 / n_windows(frames) * k
+    return {"value": audio_h / dt, "unit": "audio-hours/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{k} of {n_windows(frames)} windows of the {frames}-frame recording (adapt + final pass + "
+                      f"stitch) through oracle/ref_loop.py with model and CTC on the CPU, {dt:.1f} s"}
+
+
+def run_dae(a, rank, world, local):
+    import random
+    import torch.distributed as dist
+    from dae import _C, lib, prof, standin
+    from dae.optim import MADGRAD
+    from dae.shard import all_reduce_counts
+    from dae.wer import word_error_counts
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the dae kernels have no CPU path")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    _C.lib()
+    tok = standin.SyntheticTokenizer()
+    model = standin.build_model(tok.vocab_size(), device=dev, seed=0)
+    args = make_args(standin.default_config())
+    # two synthetic recordings per rank, alternated so no step re-reads the previous step's input
+    specs_host = [torch.randn(1, 80, a.frames, generator=torch.Generator().manual_seed(100 * rank + k)).pin_memory()
+                  for k in range(2)]
+    specs_dev = [s.to(dev) for s in specs_host]
+    standin.calibrate_blank_prior(model, specs_dev[0][:, :, :SEQ_LEN])
+    gold = [" ".join(tok.decode([i]) for i in random.Random(k).choices(range(1, 4095), k=a.frames // 40))
+            for k in range(2)]
+    audio_h = a.frames / FPS / 3600.0
+
+    def step(k, host):
+        random.seed(k)
+        torch.manual_seed(k)
+        spec = specs_host[k % 2] if host else specs_dev[k % 2]
+        ids = lib.dynamic_eval(args, model, spec, SEQ_LEN, OVERLAP, tok, use_tqdm=False, optim=MADGRAD,
+                               output="greedy")
+        counts = word_error_counts([tok.decode(ids)], [gold[k % 2]])
+        all_reduce_counts(counts, dev)
+        return ids
+
+    def timed(n_steps, host, first):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        n_ids = 0
+        for k in range(n_steps):
+            n_ids += len(step(first + k, host))
+        e.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([s.elapsed_time(e) * 1e-3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), n_ids
+
+    for k in range(a.warmup):
+        step(k, False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    prof.reset()
+    prof.enable(True)
+    l0 = _C.launch_count()
+    t_dev, _ = timed(a.steps, False, a.warmup)
+    launches = _C.launch_count() - l0
+    kern = prof.summary()
+    prof.enable(False)
+    t_e2e, n_ids = timed(a.steps, True, a.warmup + a.steps)
+    clocks = sampler.stop()
+
+    value = audio_h * a.steps * world / t_dev
+    e2e = audio_h * a.steps * world / t_e2e
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    # dominant dae op by device time: the CTC loss+grad pair (lattice launch + dense gradient launch)
+    nwin = n_windows(a.frames)
+    table = {}
+    for name, r in kern.items():
+        table[name] = {"launches_per_step": r["launches"] / a.steps, "avg_us": r["avg_ms"] * 1e3,
+                       "algorithmic_bytes_per_launch": r["bytes_per_launch"],
+                       "gbs": (r["bytes_per_launch"] / (r["avg_ms"] * 1e-3) / 1e9) if r["avg_ms"] > 0 else None}
+    roof = None
+    if "ctc_lattice" in kern and "ctc_grad" in kern:
+        t_pair = kern["ctc_lattice"]["avg_ms"] + kern["ctc_grad"]["avg_ms"]
+        by = kern["ctc_grad"]["bytes_per_launch"]                 # 2*T*N*C*4: read lp once, write grad once
+        ach = by / (t_pair * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("ctc_lattice+ctc_grad")
+        roof = {"kernel": "ctc_lattice+ctc_grad (CTC loss+grad of one adapt step, T=2048 N=1 C=4096)", "bound": "hbm",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "peak_source": peak_src, "avg_launch_us": t_pair * 1e3,
+                "note": "N=1 lattice is a 2048-step dependent chain (latency-bound); see DESIGN.md"}
+    cpu = cpu_baseline_sample(a.frames) if world == 1 else None
+    spec_bytes = a.frames * 80 * 4
+    line = {
+        "metric": "audio-hours/sec dynamic-eval", "value": value, "unit": "audio-hours/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": t_dev / a.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": value / 0.0121 if a.frames == 415990 else None, "dtype": "f32",
+        "data": "synthetic (N(0,1) log-mel stand-in, random-init weights, calibrated blank prior)",
+        "config": workload_config(a),
+        "e2e": {"value": e2e, "unit": "audio-hours/s", "h2d_bytes_per_step": spec_bytes + nwin * 8 * 700,
+                "d2h_bytes_per_step": int(nwin * 4 * 700 + 4 * n_ids / max(a.steps, 1)),
+                "ms_per_step": t_e2e / a.steps * 1e3},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": table, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dae", choices=["dae", "reference"])
+    ap.add_argument("--frames", type=int, default=120000, help="frames per synthetic recording (100 fps)")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
+        return
+    from dae.shard import init_distributed
+    rank, world, local = init_distributed()
+    if world != a.gpus and rank == 0:
+        print(f"[bench] note: --gpus {a.gpus} but WORLD_SIZE={world}; launch N>1 with torch.distributed.run",
+              file=sys.stderr)
+    run_dae(a, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,7 @@ _PROTOS = {
     "dae_launch_count": (c_int64, []),
     "dae_greedy_collapse": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dae_collapse_path": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dae_specaug_scratch_bytes": (c_size_t, []),
     "dae_specaug_repeat": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                    c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -12,7 +12,7 @@ import ctypes
 
 import torch
 
-from . import _C
+from . import _C, prof
 
 MAX_BANDS = 32
 
@@ -80,7 +80,7 @@ class SpecAugment(torch.nn.Module):
         scratch = torch.empty(lib.dae_specaug_scratch_bytes(), dtype=torch.uint8, device=dev)
         nf, nt = int(fb.shape[1]), int(tb.shape[1])
         st = _C.stream_ptr(dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), prof.span("specaug_repeat", (1 + B + n_clean) * F * T * 4):
             if n_clean:
                 # one launch pair: B masked copies + n_clean clean copies of the shared window
                 src = x[0]

@@ -13,6 +13,7 @@
 //                        accuracy in the occupancies even when |log-likelihood| ~ 1e4.
 //   ctc_grad_kernel    : one CTA per (t, n) row: dense exp(lp) minus the occupancy of the
 //                        classes that occur in the label sequence.  Pure streaming.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace dae {
@@ -20,8 +21,8 @@ namespace dae {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr double kLn2d = 0.69314718055994530942;
 constexpr int kLatThreads = 1024;
-constexpr int kMaxStatesPerThread = 8;            // S <= 8192  ->  Lmax <= 4095
-constexpr int kPrefetch = 8;                      // time steps of lp gathers in flight (even)
+constexpr int kMaxPairsPerThread = 4;             // Lmax + 1 <= 4096 label/blank state pairs
+constexpr int kLatSmemBudget = 200 * 1024;        // dynamic smem for labels + lattice rows + emission ring
 
 struct CtcScratch {           // carved out of the caller's scratch buffer
   float* alpha;               // [N][T][Sp]  centred, log2 units
@@ -30,7 +31,7 @@ struct CtcScratch {           // carved out of the caller's scratch buffer
   int32_t* leader;            // [N][Lp]  1 if first occurrence of its class
   double* off_a;              // [N][T]   alpha_t(s) = alpha[t][s] + off_a[t]   (log2 units)
   double* off_b;              // [N][T]   beta_t(s)  = beta_rev[t][S-1-s] + off_b[t]
-  double* ll2;                // [2][N]   log2-likelihood from the alpha CTA, then from the beta CTA
+  double* ll2;                // [4][N]   log2-likelihood from the alpha CTA, the beta CTA, then debug totals
   int Sp, Lp;
 };
 
@@ -50,7 +51,7 @@ static inline size_t ctc_carve(CtcScratch& s, void* base, int T, int N, int Lmax
   const size_t offs = align_up((size_t)N * T * sizeof(double), 256);
   s.off_a = (double*)(p + off); off += offs;
   s.off_b = (double*)(p + off); off += offs;
-  s.ll2 = (double*)(p + off); off += align_up((size_t)2 * N * sizeof(double), 256);
+  s.ll2 = (double*)(p + off); off += align_up((size_t)4 * N * sizeof(double), 256);
   return off;
 }
 
@@ -79,19 +80,114 @@ __device__ __forceinline__ int f2ord(float f) {
 }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
-template <int K>
+// ---- mbarrier / bulk-copy (TMA) helpers -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion is counted on `bar`.
+__device__ __forceinline__ void tma_row_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// Fallback for rows that are not 16-byte aligned: per-thread 4-byte cp.async, tracked by the same mbarrier.
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// log2(2^a + 2^b), 2 MUFU ops.
+__device__ __forceinline__ float lse2_2(float a, float b) {
+  const float m = fmaxf(a, b), lo = fminf(a, b);
+  if (m == -CUDART_INF_F) return m;
+  return m + fast_lg2(1.0f + fast_ex2(lo - m));
+}
+
+struct LatSmem {              // byte offsets into dynamic shared memory (host and device agree)
+  int bars, cx, wmx, lab, a0, a1, rows, row_stride, stages, total;
+};
+__host__ __device__ inline LatSmem lat_smem_layout(int C, int Lp, int Sp, int max_bytes) {
+  LatSmem m;
+  m.bars = 0;                                            // up to 16 mbarriers
+  m.cx = 16 * 8;                                         // float2[4]: (centring constant, blank emission) per step slot
+  m.wmx = m.cx + 4 * 8;                                  // int[4][32]: per-warp maxima per step slot
+  m.lab = m.wmx + 4 * 32 * 4;
+  m.a0 = (int)align_up((size_t)m.lab + (size_t)Lp * 4, 16);
+  m.a1 = m.a0 + (Sp + 4) * 4;
+  m.rows = (int)align_up((size_t)m.a1 + (size_t)(Sp + 4) * 4, 128);
+  m.row_stride = (int)align_up((size_t)C * 4, 128);
+  int st = (max_bytes - m.rows) / m.row_stride;
+  m.stages = st > 16 ? 16 : st;
+  m.total = m.rows + m.stages * m.row_stride;
+  return m;
+}
+
+// One lattice step for the P state pairs of a consumer thread.  `prev`/`cur` are the ping-pong
+// lattice rows, `xrow` the emission row of this frame in the smem ring, cx = (c, xb).
+template <int P>
+__device__ __forceinline__ void lattice_step(const float* __restrict__ prev, float* __restrict__ cur,
+                                             const float* __restrict__ xrow, float2 cx, float* __restrict__ orow,
+                                             const int (&xoff)[P], const bool (&skip)[P], const int (&pidx)[P],
+                                             int L, int* __restrict__ wmx_slot, int warp, int lane) {
+  float vmax = -CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int p = pidx[j];
+    if (p <= L) {
+      const float pm1 = prev[2 * p - 1];
+      const float2 pp = *reinterpret_cast<const float2*>(prev + 2 * p);     // (blank, label) of this pair
+      const float xl = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(xrow) + xoff[j]);
+      const float vb = cx.y + lse2_2(pp.x, pm1);
+      float vl = -CUDART_INF_F;
+      if (p < L) vl = fmaf(xl, kLog2e, -cx.x) + lse3_2(pp.y, pp.x, skip[j] ? pm1 : -CUDART_INF_F);
+      *reinterpret_cast<float2*>(cur + 2 * p) = make_float2(vb, vl);
+      if (p < L) *reinterpret_cast<float2*>(orow + 2 * p) = make_float2(vb, vl);
+      else orow[2 * p] = vb;
+      vmax = fmaxf(vmax, fmaxf(vb, vl));
+    }
+  }
+  const int wmax = __reduce_max_sync(0xffffffffu, f2ord(vmax));
+  if (lane == 0) wmx_slot[warp] = wmax;
+}
+
+// One CTA per (sample, direction): `NTc` consumer threads + one producer warp (the last warp).
+// Consumer thread i owns the state pairs p = i + j*NTc: the blank state 2p and the label state
+// 2p+1, so the blank emission is a broadcast and only label states gather from the emission row.
+// The producer warp keeps a ring of `stages` emission rows filled with TMA bulk copies (one 1-D
+// copy per frame), waits for the next row so consumers never poll an mbarrier, reduces the
+// per-warp maxima of step t-1 into the centring constant of step t+1 and accumulates the removed
+// offsets in fp64.  One __syncthreads() per frame is the only CTA-wide synchronisation.
+template <int P>
 __global__ void __launch_bounds__(kLatThreads, 1)
 ctc_lattice_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, int C,
                    const int64_t* __restrict__ tgt, int64_t tgt_stride, int Lmax,
                    const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len, int blank,
-                   float* __restrict__ nll, CtcScratch sc) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int mx[4];                   // rotating per-step maxima (ordered-int encoding)
+                   float* __restrict__ nll, CtcScratch sc, LatSmem lay, int vec) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = blockIdx.y;
   const int N = gridDim.y;
   const int dir = blockIdx.x;             // 0 alpha, 1 beta
-  const int NT = blockDim.x;
+  const int NTc = blockDim.x - 32;        // consumer threads
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const bool producer = tid >= NTc;
+  const int n_cwarps = NTc >> 5;
+  const int R = lay.stages;
 
   int L = (int)tgt_len[n];
   L = L < 0 ? 0 : (L > Lmax ? Lmax : L);
@@ -99,25 +195,113 @@ ctc_lattice_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, 
   Tn = Tn < 0 ? 0 : (Tn > T ? T : Tn);
   const int S = 2 * L + 1;
 
-  // smem: labels (direction-ordered) then two lattice rows padded on the left.
-  int* lab = reinterpret_cast<int*>(smem_raw);                       // [Lp]
-  float* a0 = reinterpret_cast<float*>(lab + sc.Lp) + 4;             // [-4 .. Sp)
-  float* a1 = a0 + sc.Sp + 4;                                        // [-4 .. Sp)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);
+  float2* cxs = reinterpret_cast<float2*>(smem_raw + lay.cx);         // [4]
+  int* wmx = reinterpret_cast<int*>(smem_raw + lay.wmx);              // [4][32]
+  int* lab = reinterpret_cast<int*>(smem_raw + lay.lab);              // [Lp] direction-ordered labels
+  float* a0 = reinterpret_cast<float*>(smem_raw + lay.a0) + 4;        // [-4 .. Sp)
+  float* a1 = reinterpret_cast<float*>(smem_raw + lay.a1) + 4;
+  unsigned char* rows = smem_raw + lay.rows;
 
-  for (int k = tid; k < L; k += NT) {
+  if (Tn == 0) {  // degenerate: empty input.  Feasible only for the empty target.
+    if (tid == 0) {
+      const double ll = (L == 0) ? 0.0 : -(double)CUDART_INF_F;
+      sc.ll2[dir * N + n] = ll;
+      if (dir == 0) nll[n] = (float)(-ll);
+    }
+    return;
+  }
+
+  for (int k = tid; k < L; k += blockDim.x) {
     const int src = dir ? (L - 1 - k) : k;
     lab[k] = (int)tgt[n * tgt_stride + src];
   }
   if (tid < 4) {
     a0[tid - 4] = -CUDART_INF_F;
     a1[tid - 4] = -CUDART_INF_F;
-    mx[tid] = f2ord(-CUDART_INF_F);
+  }
+  for (int i = tid; i < 128; i += blockDim.x) wmx[i] = f2ord(-CUDART_INF_F);
+  if (tid == 0) {
+    for (int r = 0; r < R; ++r) mbar_init(&full[r], vec ? 1u : 32u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
+  const float* base = lp + n * sN;
+  float* out = (dir ? sc.beta_rev : sc.alpha) + (int64_t)n * T * sc.Sp;
+  const int64_t ostep = dir ? -(int64_t)sc.Sp : (int64_t)sc.Sp;      // output row advance per lattice step
+  const int64_t xstep = dir ? -sT : sT;                               // input row advance per lattice step
+  const int64_t t_first = dir ? (Tn - 1) : 0;
+
+  if (producer) {
+    // ------------------------------------------------------------------ producer warp
+    double* offs = (dir ? sc.off_b : sc.off_a) + (int64_t)n * T;
+    const uint32_t row_bytes = (uint32_t)C * 4u;
+    auto fill = [&](int slot, const float* src) {
+      float* dst = reinterpret_cast<float*>(rows + (size_t)slot * lay.row_stride);
+      if (vec) {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full[slot], row_bytes);
+          tma_row_g2s(dst, src, row_bytes, &full[slot]);
+        }
+      } else {
+        for (int i = lane; i < C; i += 32) cp_async4(dst + i, src + i);
+        cp_async_arrive(&full[slot]);
+      }
+    };
+    const float* src_next = base + t_first * sT;      // row of the next lattice step to enqueue
+    int t_fill = 0;
+    for (; t_fill < R && t_fill < Tn; ++t_fill, src_next += xstep) fill(t_fill, src_next);
+    int fill_slot = 0;                                 // slot that frees up after the current step
+
+    // step 0 constants
+    mbar_wait(&full[0], 0);
+    if (lane == 0) {
+      cxs[0] = make_float2(0.0f, reinterpret_cast<const float*>(rows)[blank] * kLog2e);
+      offs[t_first] = 0.0;
+    }
+    __syncthreads();                                   // "start": consumers may run step 0
+
+    double off_acc = 0.0;
+    int wslot = 1 % R;                                 // ring slot of step t+1
+    uint32_t wphase = (1 / R) & 1;
+    int64_t tt_next = t_first + (dir ? -1 : 1);        // actual frame index of step t+1
+    for (int t = 0; t < Tn; ++t) {
+      if (t + 1 < Tn) {
+        mbar_wait(&full[wslot], wphase);
+        // centring constant of step t+1: maximum over the lattice at step t-1 (lag 2)
+        float c = 0.0f;
+        if (t >= 1) {
+          int v = (lane < n_cwarps) ? wmx[((t - 1) & 3) * 32 + lane] : f2ord(-CUDART_INF_F);
+          v = __reduce_max_sync(0xffffffffu, v);
+          c = ord2f(v);
+          if (c == -CUDART_INF_F) c = 0.0f;
+        }
+        if (lane == 0) {
+          off_acc += (double)c;
+          offs[tt_next] = off_acc;
+          const float xbl = reinterpret_cast<const float*>(rows + (size_t)wslot * lay.row_stride)[blank];
+          cxs[(t + 1) & 3] = make_float2(c, fmaf(xbl, kLog2e, -c));
+        }
+        if (++wslot == R) { wslot = 0; wphase ^= 1u; }
+        tt_next += dir ? -1 : 1;
+      }
+      __syncthreads();                                 // end of step t
+      if (t_fill < Tn) {                               // the slot consumed at step t is free for step t+R
+        fill(fill_slot, src_next);
+        src_next += xstep;
+        ++t_fill;
+      }
+      if (++fill_slot == R) fill_slot = 0;
+    }
+    if (lane == 0) sc.ll2[2 * N + dir * N + n] = off_acc;   // total removed offset (consumer 0 adds the tail)
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumer threads
   // Label grouping for the gradient pass (alpha CTA only): first occurrence + next occurrence.
   if (dir == 0) {
-    for (int k = tid; k < L; k += NT) {
+    for (int k = tid; k < L; k += NTc) {
       const int c = lab[k];
       int nxt = -1;
       for (int j = k + 1; j < L; ++j)
@@ -129,107 +313,77 @@ ctc_lattice_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, 
       sc.leader[(int64_t)n * sc.Lp + k] = first;
     }
   }
-
-  // Per-thread state constants.  State s (direction order): class and whether the s-2 skip is legal.
-  int cls[K];
-  bool skip[K];
+  int xoff[P], pidx[P];
+  bool skip[P];
 #pragma unroll
-  for (int j = 0; j < K; ++j) {
-    const int s = tid + j * NT;
-    cls[j] = blank;
+  for (int j = 0; j < P; ++j) {
+    const int p = tid + j * NTc;
+    pidx[j] = p;
+    xoff[j] = blank * 4;
     skip[j] = false;
-    if (s < S && (s & 1)) {
-      const int k = s >> 1;
-      cls[j] = lab[k];
-      skip[j] = (k >= 1) && (lab[k - 1] != cls[j]);
+    if (p < L) {
+      xoff[j] = lab[p] * 4;
+      skip[j] = (p >= 1) && (lab[p - 1] != lab[p]);
     }
   }
+  float* orow = out + t_first * sc.Sp;
+  __syncthreads();                                     // "start": step-0 constants are in smem
 
-  float* out = (dir ? sc.beta_rev : sc.alpha) + (int64_t)n * T * sc.Sp;
-  double* offs = (dir ? sc.off_b : sc.off_a) + (int64_t)n * T;
-  const float* base = lp + n * sN;
-
-  if (Tn == 0) {  // degenerate: empty input.  Feasible only for the empty target.
-    if (tid == 0) {
-      const double ll = (L == 0) ? 0.0 : -(double)CUDART_INF_F;
-      sc.ll2[dir * N + n] = ll;
-      if (dir == 0) nll[n] = (float)(-ll);
-    }
-    return;
-  }
-
-  // Register ring of prefetched emissions: xr[u][j] = lp[time(u), cls[j]].
-  float xr[kPrefetch][K];
+  // step 0: only states 0 and 1 are reachable
+  {
+    const float* xrow = reinterpret_cast<const float*>(rows);
+    const float2 cx = cxs[0];
+    float vmax = -CUDART_INF_F;
 #pragma unroll
-  for (int u = 0; u < kPrefetch; ++u) {
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      xr[u][j] = 0.0f;
-      if (u < Tn && tid + j * NT < S) {
-        const int tt = dir ? (Tn - 1 - u) : u;
-        xr[u][j] = __ldg(base + tt * sT + cls[j]);
+    for (int j = 0; j < P; ++j) {
+      const int p = pidx[j];
+      if (p <= L) {
+        const float vb = (p == 0) ? cx.y : -CUDART_INF_F;
+        float vl = -CUDART_INF_F;
+        if (p == 0 && L > 0) vl = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(xrow) + xoff[j]) * kLog2e;
+        *reinterpret_cast<float2*>(a0 + 2 * p) = make_float2(vb, vl);
+        if (p < L) *reinterpret_cast<float2*>(orow + 2 * p) = make_float2(vb, vl);
+        else orow[2 * p] = vb;
+        vmax = fmaxf(vmax, fmaxf(vb, vl));
       }
     }
+    const int wmax = __reduce_max_sync(0xffffffffu, f2ord(vmax));
+    if (lane == 0) wmx[warp] = wmax;
+    orow += ostep;
+    __syncthreads();
   }
-
-  double off_acc = 0.0;                    // thread 0: sum of the centring constants so far
-  for (int t0 = 0; t0 < Tn; t0 += kPrefetch) {
-#pragma unroll
-    for (int u = 0; u < kPrefetch; ++u) {
-      const int t = t0 + u;
-      if (t < Tn) {                        // uniform across the CTA
-        float* cur = (u & 1) ? a1 : a0;    // t0 is a multiple of kPrefetch (even)
-        const float* prev = (u & 1) ? a0 : a1;
-        const int tt = dir ? (Tn - 1 - t) : t;
-        float* orow = out + (int64_t)tt * sc.Sp;
-        // centring constant: the maximum of the previous step's values (0 at t = 0 / dead lattice)
-        float c = 0.0f;
-        if (t > 0) {
-          c = ord2f(mx[t & 3]);
-          if (c == -CUDART_INF_F) c = 0.0f;
-        }
-        if (tid == 0) {
-          off_acc += (double)c;
-          offs[tt] = off_acc;
-          mx[(t + 2) & 3] = f2ord(-CUDART_INF_F);   // last read at step t-2, next filled at step t+1
-        }
-        float vmax = -CUDART_INF_F;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-          const int s = tid + j * NT;
-          if (s < S) {
-            const float x = xr[u][j] * kLog2e;
-            float v;
-            if (t == 0) {
-              v = (s <= 1) ? x : -CUDART_INF_F;
-            } else {
-              const float p0 = prev[s], p1 = prev[s - 1];
-              const float p2 = skip[j] ? prev[s - 2] : -CUDART_INF_F;
-              v = (x - c) + lse3_2(p0, p1, p2);
-            }
-            cur[s] = v;
-            orow[s] = v;
-            vmax = fmaxf(vmax, v);
-            // refill this ring slot with the emission kPrefetch steps ahead
-            const int tn = t + kPrefetch;
-            if (tn < Tn) {
-              const int ttn = dir ? (Tn - 1 - tn) : tn;
-              xr[u][j] = __ldg(base + ttn * sT + cls[j]);
-            }
-          }
-        }
-        const int wmax = __reduce_max_sync(0xffffffffu, f2ord(vmax));
-        if ((tid & 31) == 0) atomicMax(&mx[(t + 1) & 3], wmax);
-        __syncthreads();
-      }
-    }
+  int slot = 1 % R;
+  const unsigned char* xrow_b = rows + (size_t)slot * lay.row_stride;
+  const unsigned char* rows_end = rows + (size_t)R * lay.row_stride;
+  int t = 1;
+  for (; t + 1 < Tn; t += 2) {                         // two steps per trip: static ping-pong buffers
+    lattice_step<P>(a0, a1, reinterpret_cast<const float*>(xrow_b), cxs[t & 3], orow, xoff, skip, pidx, L,
+                    wmx + (t & 3) * 32, warp, lane);
+    orow += ostep;
+    xrow_b += lay.row_stride;
+    if (xrow_b == rows_end) xrow_b = rows;
+    __syncthreads();
+    lattice_step<P>(a1, a0, reinterpret_cast<const float*>(xrow_b), cxs[(t + 1) & 3], orow, xoff, skip, pidx, L,
+                    wmx + ((t + 1) & 3) * 32, warp, lane);
+    orow += ostep;
+    xrow_b += lay.row_stride;
+    if (xrow_b == rows_end) xrow_b = rows;
+    __syncthreads();
+  }
+  if (t < Tn) {                                        // odd tail (t is odd here: a0 -> a1)
+    lattice_step<P>(a0, a1, reinterpret_cast<const float*>(xrow_b), cxs[t & 3], orow, xoff, skip, pidx, L,
+                    wmx + (t & 3) * 32, warp, lane);
+    __syncthreads();
   }
 
   if (tid == 0) {
     const float* last = ((Tn - 1) & 1) ? a1 : a0;
     const float e1 = last[S - 1];
     const float e2 = (S > 1) ? last[S - 2] : -CUDART_INF_F;
-    const double ll2 = off_acc + (double)lse3_2(e1, e2, -CUDART_INF_F);
+    // total offset = off_a/off_b of the last processed frame, written by the producer before the last barrier
+    const double* offs = (dir ? sc.off_b : sc.off_a) + (int64_t)n * T;
+    const double off_last = (Tn > 1) ? offs[dir ? 0 : (Tn - 1)] : 0.0;
+    const double ll2 = off_last + (double)lse2_2(e1, e2);
     sc.ll2[dir * N + n] = ll2;
     if (dir == 0) nll[n] = (float)(-ll2 * kLn2d);
   }
@@ -316,13 +470,13 @@ ctc_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, int
   }
 }
 
-template <int K>
-static int launch_lattice(int NT, size_t smem, cudaStream_t st, int N, const float* lp, int64_t sT, int64_t sN, int T, int C,
-                          const int64_t* tgt, int64_t tgt_stride, int Lmax, const int64_t* in_len,
-                          const int64_t* tgt_len, int blank, float* nll, const CtcScratch& sc) {
-  if (smem > 48 * 1024)
-    DAE_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ctc_lattice_kernel<K><<<dim3(2, N), NT, smem, st>>>(lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, nll, sc);
+template <int P>
+static int launch_lattice(int NT, const LatSmem& lay, int vec, cudaStream_t st, int N, const float* lp, int64_t sT,
+                          int64_t sN, int T, int C, const int64_t* tgt, int64_t tgt_stride, int Lmax,
+                          const int64_t* in_len, const int64_t* tgt_len, int blank, float* nll, const CtcScratch& sc) {
+  DAE_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+  ctc_lattice_kernel<P><<<dim3(2, N), NT, lay.total, st>>>(lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len,
+                                                          blank, nll, sc, lay, vec);
   DAE_LAUNCH_OK();
   return 0;
 }
@@ -339,7 +493,7 @@ static int ctc_check(const float* lp, int T, int N, int C, const int64_t* tgt, i
                      const int64_t* tgt_len, int blank, const void* scratch, size_t scratch_bytes) {
   if (!lp || !in_len || !tgt_len || T < 0 || N < 0 || C <= 0 || Lmax < 0 || blank < 0 || blank >= C) return DAE_E_BADARG;
   if (Lmax > 0 && !tgt) return DAE_E_BADARG;
-  if (2 * Lmax + 1 > dae::kLatThreads * dae::kMaxStatesPerThread) return DAE_E_TOOBIG;
+  if (Lmax + 1 > (dae::kLatThreads - 32) * dae::kMaxPairsPerThread) return DAE_E_TOOBIG;
   if (!scratch || scratch_bytes < dae_ctc_scratch_bytes(T, N, Lmax)) return DAE_E_SCRATCH;
   if ((reinterpret_cast<uintptr_t>(scratch) & 255u) != 0) return DAE_E_ALIGN;
   return 0;
@@ -355,17 +509,24 @@ extern "C" int dae_ctc_lattice(const float* lp, int64_t sT, int64_t sN, int T, i
   if (N == 0) return 0;
   CtcScratch sc;
   ctc_carve(sc, scratch, T, N, Lmax);
-  const int S = 2 * Lmax + 1;
-  int NT = ((S + 31) / 32) * 32;
-  if (NT > kLatThreads) NT = kLatThreads;
-  const int K = (S + NT - 1) / NT;
-  const size_t smem = (size_t)sc.Lp * 4 + 2 * (size_t)(sc.Sp + 4) * 4;
+  const int pairs = Lmax + 1;
+  constexpr int kMaxConsumers = kLatThreads - 32;        // one warp is the TMA producer
+  int P = (pairs + kMaxConsumers - 1) / kMaxConsumers;
+  P = P <= 1 ? 1 : (P <= 2 ? 2 : 4);
+  if (pairs > 320 && P == 1) P = 2;                      // fewer, fatter warps: less issue pressure per step
+  if (const char* e = getenv("DAE_CTC_PAIRS")) {         // tuning override (1, 2 or 4 pairs per thread)
+    const int q = atoi(e);
+    if ((q == 1 || q == 2 || q == 4) && (pairs + q - 1) / q <= kMaxConsumers) P = q;
+  }
+  int NT = (((pairs + P - 1) / P + 31) / 32) * 32 + 32;  // consumers + producer warp
+  const LatSmem lay = lat_smem_layout(C, sc.Lp, sc.Sp, kLatSmemBudget);
+  if (lay.stages < 2) return DAE_E_TOOBIG;
+  const int vec = aligned16(lp) && (C % 4 == 0) && (sT % 4 == 0) && (sN % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
-#define DAE_LAT(KK) return launch_lattice<KK>(NT, smem, st, N, lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, nll, sc)
-  if (K <= 1) DAE_LAT(1);
-  if (K <= 2) DAE_LAT(2);
-  if (K <= 4) DAE_LAT(4);
-  DAE_LAT(8);
+#define DAE_LAT(PP) return launch_lattice<PP>(NT, lay, vec, st, N, lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, nll, sc)
+  if (P <= 1) DAE_LAT(1);
+  if (P <= 2) DAE_LAT(2);
+  DAE_LAT(4);
 #undef DAE_LAT
 }
 

@@ -161,3 +161,13 @@ extern "C" int dae_greedy_collapse(const float* lp, int64_t sB, int64_t sT, int 
   DAE_LAUNCH_OK();
   return 0;
 }
+
+extern "C" int dae_collapse_path(const int32_t* path, int B, int T, const int32_t* lengths, int blank,
+                                 int32_t* ids, int32_t* n_ids, void* stream) {
+  using namespace dae;
+  if (!path || !ids || !n_ids || B < 0 || T < 0) return DAE_E_BADARG;
+  if (B == 0) return 0;
+  collapse_kernel<<<B, kCollapseThreads, 0, (cudaStream_t)stream>>>(path, T, blank, lengths, ids, n_ids);
+  DAE_LAUNCH_OK();
+  return 0;
+}

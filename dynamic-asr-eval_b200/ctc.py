@@ -8,7 +8,7 @@ read of ``log_probs`` and one write of its gradient.
 """
 import torch
 
-from . import _C
+from . import _C, prof
 
 
 class _CTCFunction(torch.autograd.Function):
@@ -48,7 +48,7 @@ class _CTCFunction(torch.autograd.Function):
         nbytes = lib.dae_ctc_scratch_bytes(T, N, Lmax)
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         nll = torch.empty(N, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), prof.span("ctc_lattice", T * N * C * 4):
             rc = lib.dae_ctc_lattice(lp.data_ptr(), lp.stride(0), lp.stride(1), T, N, C,
                                      tg.data_ptr() if Lmax else None, tg.stride(0), Lmax,
                                      in_len.data_ptr(), tg_len.data_ptr(), int(blank),
@@ -72,7 +72,7 @@ class _CTCFunction(torch.autograd.Function):
             g = g.contiguous()
             g_stride = 1
         grad = torch.empty((T, N, C), dtype=torch.float32, device=lp.device)
-        with torch.cuda.device(lp.device):
+        with torch.cuda.device(lp.device), prof.span("ctc_grad", 2 * T * N * C * 4):
             rc = _C.lib().dae_ctc_grad(lp.data_ptr(), lp.stride(0), lp.stride(1), T, N, C,
                                        tg.data_ptr() if Lmax else None, tg.stride(0), Lmax,
                                        in_len.data_ptr(), tg_len.data_ptr(), ctx.blank,

@@ -9,7 +9,7 @@ only the collapsed ids (<= T int32) cross PCIe.
 """
 import torch
 
-from . import _C
+from . import _C, prof
 
 
 def greedy_ids_device(emission: torch.Tensor, blank_id: int, lengths: torch.Tensor = None):
@@ -29,12 +29,26 @@ def greedy_ids_device(emission: torch.Tensor, blank_id: int, lengths: torch.Tens
     n_ids = torch.empty((B,), dtype=torch.int32, device=dev)
     if lengths is not None:
         lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), prof.span("greedy_collapse", B * T * C * 4):
         rc = _C.lib().dae_greedy_collapse(x.data_ptr(), x.stride(0), x.stride(1), B, T, C, _C.ptr(lengths),
                                           int(blank_id), path.data_ptr(), ids.data_ptr(), n_ids.data_ptr(),
                                           _C.stream_ptr(dev))
     _C.check(rc, "dae_greedy_collapse")
     return path, ids, n_ids
+
+
+def collapse_path_device(path: torch.Tensor, blank_id: int):
+    """Collapse an already computed per-frame argmax path [T] int32 (dae_stitch's fused output)."""
+    _C.require_cuda(path, "path")
+    p = path.detach().to(torch.int32).contiguous().reshape(1, -1)
+    T = int(p.shape[1])
+    ids = torch.empty((1, max(T, 1)), dtype=torch.int32, device=p.device)
+    n = torch.empty((1,), dtype=torch.int32, device=p.device)
+    with torch.cuda.device(p.device):
+        rc = _C.lib().dae_collapse_path(p.data_ptr(), 1, T, None, int(blank_id), ids.data_ptr(), n.data_ptr(),
+                                        _C.stream_ptr(p.device))
+    _C.check(rc, "dae_collapse_path")
+    return ids[0, :int(n[0].item())].tolist()
 
 
 def greedy_ids(emission: torch.Tensor, blank_id: int):

@@ -1,0 +1,361 @@
+"""Dynamic-evaluation library with the reference's entry points (lcasr/lib.py), on the dae kernels.
+
+``dynamic_eval`` / ``dynamic_eval_ctc_loss`` (lib.py:450-643), ``AWMC`` (:206-376),
+``prepare_chunks`` (:128-145), the kwarg getters (:102-125,419-428), ``apply_args``
+(:1756-1787) and ``load_beamsearch`` (:37-72) keep their signatures, so
+``run_dynamic_eval_full.py`` works with ``import dae.lib as lib``.
+
+What changed underneath (same arithmetic, different placement):
+  * the spectrogram is copied to the GPU once; windows are device views (the reference builds and
+    augments every window on the CPU and copies [2,80,16384] per step, lib.py:538-549);
+  * SpecAugment + the ``repeat(2,1,1)`` batch build is one kernel pair (dae_specaug_repeat);
+  * pseudo-labels come from the greedy kernel on the device posteriors; only the collapsed ids
+    cross PCIe for the tokenizer's decode -> re-encode round trip (lib.py:559,569 copy 33.5 MB
+    twice per step to the host);
+  * CTC loss/grad run in dae_ctc_lattice + dae_ctc_grad;
+  * final-pass window posteriors stay on the device and are stitched by dae_stitch (the reference
+    keeps ~6.6 GB of host copies and two ~2 GB host accumulators for a 69 min recording).
+"""
+import argparse
+import ast
+import random
+import time
+from functools import partial
+from typing import Callable
+
+import torch
+import torch.nn as nn
+
+from . import _C
+from .augment import SpecAugment
+from .ctc import CTCLoss
+from .greedy import GreedyCTCDecoder, greedy_ids_device
+from .optim import MADGRAD
+from .stitch import stitch_flat, window_positions
+
+
+# ----------------------------------------------------------------------------- kwarg getters
+def get_specaugment_config_from_args(args):
+    """lcasr/lib.py:102-112."""
+    a = {k.replace('spec_augment_', ''): v for k, v in args.__dict__.items() if k.startswith('spec_augment')}
+    return {
+        'n_time_masks': a.get('n_time_masks', 0),
+        'n_freq_masks': a.get('n_freq_masks', 0),
+        'freq_mask_param': a.get('freq_mask_param', 42),
+        'time_mask_param': a.get('time_mask_param', -1),
+        'min_p': a.get('min_p', 0.05),
+        'zero_masking': a.get('zero_masking', False),
+    }
+
+
+def get_frame_shuffle_config_from_args(args):
+    """lcasr/lib.py:114-120."""
+    a = {k.replace('frame_shuffle_', ''): v for k, v in args.__dict__.items() if k.startswith('frame_shuffle')}
+    return {'time_dimension': a.get('time_dimension', False), 'freq_dimension': a.get('freq_dimension', False)}
+
+
+def get_lr_args_from_args(args):
+    """lcasr/lib.py:122-125."""
+    lr_args = {k.replace('optim_', ''): v for k, v in args.__dict__.items() if k.startswith('optim_')}
+    lr_args['lr'] = lr_args.get('lr', 9e-5)
+    return lr_args
+
+
+def get_cutout_params_from_args(args, seq_len):
+    """lcasr/lib.py:419-428."""
+    a = {k.replace('cutout_', ''): v for k, v in args.__dict__.items() if k.startswith('cutout')}
+    return {'seq_len': seq_len, 'cutout_val': a.get('value', 'mean'), 'num_rectangles': a.get('num_rectangles', 0),
+            'max_width': a.get('max_width', 100), 'max_height': a.get('max_height', 10)}
+
+
+def prepare_chunks(spec, seq_len, overlap):
+    """lcasr/lib.py:128-145: windows of ``seq_len`` frames every ``seq_len-overlap`` frames; the first
+    window shorter than its predecessor is kept and ends the list.  Values are views of ``spec``."""
+    spec_n = spec.shape[-1]
+    last_ulen, kill_next = None, False
+    if spec_n <= seq_len:
+        return {0: spec}, [0]
+    training_data = {}
+    for i in range(0, spec_n, seq_len - overlap):
+        audio_chunk = spec[:, :, i:i + seq_len]
+        u_len = audio_chunk.shape[-1]
+        if kill_next:
+            break
+        elif last_ulen is not None and u_len < last_ulen:
+            kill_next = True
+        last_ulen = u_len
+        training_data[i] = audio_chunk
+    return training_data, list(training_data.keys())
+
+
+def frame_shuffle(spec, time_dimension=False, freq_dimension=False):
+    """lcasr/lib.py:81-84 (device tensors work as is)."""
+    if time_dimension:
+        spec = spec[:, :, torch.randperm(spec.shape[-1], device=spec.device)]
+    if freq_dimension:
+        spec = spec[:, torch.randperm(spec.shape[-2], device=spec.device), :]
+    return spec
+
+
+def add_random_noise(spec, noise_factor):
+    """lcasr/lib.py:379-382."""
+    if noise_factor == 0:
+        return spec
+    noise = torch.normal(0, std=spec.std().item(), size=spec.shape, device=spec.device)
+    return spec + noise * noise_factor
+
+
+def _freeze(model, args):
+    """lcasr/lib.py:163-204 (the three CLI freeze switches)."""
+    d = args.__dict__
+    if d.get('freeze_subsampling', False):
+        for p in model.subsampling.parameters():
+            p.requires_grad = False
+    if d.get('freeze_all_but_last_block_and_head', False):
+        for p in model.parameters():
+            p.requires_grad = False
+        for p in list(model.layers[-1].parameters()) + list(model.decoder.parameters()):
+            p.requires_grad = True
+    if d.get('train_subsampling_only', False):
+        for p in model.parameters():
+            p.requires_grad = False
+        for p in model.subsampling.parameters():
+            p.requires_grad = True
+    return model
+
+
+class _Timer:
+    """Per-phase host+device timings of one dynamic_eval call (``args.print_runtimes``)."""
+
+    def __init__(self):
+        self.t = {}
+
+    def add(self, key, dt):
+        self.t[key] = self.t.get(key, 0.0) + dt
+
+
+def _pseudo_targets(lp_teacher, blank, tokenizer, beam_search_fn, beams):
+    """Greedy (device kernel) or beam-search pseudo-labels -> python id list after the tokenizer's
+    decode -> re-encode round trip (lcasr/lib.py:558-569)."""
+    if beam_search_fn is None or beams == 0:
+        _, ids, n = greedy_ids_device(lp_teacher, blank)
+        k = int(n[0].item())                               # the one host sync of the step
+        text = tokenizer.decode(ids[0, :k].tolist())
+    else:
+        bs = beam_search_fn(log_probs=lp_teacher.detach(), beam_width=beams)
+        bs.run_search(use_tqdm=False)
+        text = bs.return_text(idx=0)
+    return text, tokenizer.encode(text)
+
+
+def dynamic_eval_ctc_loss(
+        args,
+        model: nn.Module,
+        spec: torch.Tensor,
+        seq_len: int,
+        overlap: int,
+        tokenizer,
+        use_tqdm=True,
+        optim=MADGRAD,
+        optimizer_state: dict = None,
+        beam_search_fn: Callable = None,
+        return_params: bool = False,
+        output: str = "numpy",
+):
+    """lcasr/lib.py:450-640.  ``output``: 'numpy' (reference behaviour: [N,C] float32 log-probs on the
+    host), 'device' (same tensor left on the GPU) or 'greedy' (collapsed ids of the stitched
+    posteriors as a python list — what run_dynamic_eval_full.py:100 computes next)."""
+    device = model.device
+    if torch.device(device).type != "cuda":
+        raise _C.DaeError("dae.lib.dynamic_eval needs the model on a CUDA device: there is no CPU path")
+    spec_n = spec.shape[-1]
+    downsampling_factor = args.config['model']['subsampling_factor']
+    seq_len = seq_len if seq_len != -1 else args.config['audio_chunking']['size']
+    d = args.__dict__
+    verbose = d.get('verbose', False)
+
+    spec_augment_config = get_specaugment_config_from_args(args)
+    random_noise = d.get('random_noise', 0.0)
+    lr_args = get_lr_args_from_args(args)
+    frame_shuffle_args = get_frame_shuffle_config_from_args(args)
+    cutout_args = get_cutout_params_from_args(args, seq_len)
+    if cutout_args['num_rectangles'] or any(k.startswith('entropy_augmentation_') and d[k] for k in d):
+        raise _C.DaeError("cutout / entropy_augmentation are not on the B200 hot path yet (SURVEY.md §8f-3)")
+    num_negatives = 1
+
+    # parameter snapshot: on-device clone (lib.py:482-483 clones to the CPU; restore semantics are the same)
+    params = list(model.parameters())
+    original = [p.detach().clone() for p in params]
+    req_grad = [p.requires_grad for p in params]
+    model = _freeze(model, args)
+
+    blank = model.decoder.num_classes - 1
+    ctc_loss_fn = CTCLoss(blank=blank, reduction='sum')
+    optimizer = optim([p for p in model.parameters() if p.requires_grad], **lr_args)
+    if optimizer_state is not None:
+        optimizer.load_state_dict(optimizer_state)
+    augmentation = SpecAugment(**spec_augment_config)
+
+    if seq_len > spec_n:
+        seq_len, overlap = spec_n, 0
+    else:
+        overlap = overlap if overlap != -1 else args.config['audio_chunking']['overlap']
+    assert args.config['training'].get("max_seq_len", 0) == 0, 'caching is not used anymore'
+    assert overlap / downsampling_factor == overlap // downsampling_factor, \
+        'Overlap must be a multiple of the downsampling factor'
+
+    epochs = d.get('epochs', 1)
+    shuffle = d.get('shuffle', False)
+    online = d.get('online', False)
+    beams = d.get('lm_tta_beams', 3)
+    shuffle = False if online else shuffle
+    print_runtimes = d.get('print_runtimes', False)
+    tm = _Timer()
+
+    # one H2D copy of the whole recording; windows are device views
+    t0 = time.perf_counter()
+    spec_dev = spec.to(device, non_blocking=True) if not spec.is_cuda else spec
+    if spec_dev.dtype != torch.float32:
+        spec_dev = spec_dev.float()
+    model.eval()                                            # don't update batchrenorm (lib.py:524)
+    training_data, training_keys = prepare_chunks(spec_dev, seq_len, overlap)
+    tm.add('h2d', time.perf_counter() - t0)
+
+    C = model.decoder.num_classes
+    kept = {}                                               # online: teacher posteriors of each window
+    step_log = []
+    for epoch in range(d.get('epochs', 1)):                 # lib.py:528 uses args.epochs even when online (:516 unused)
+        keys = list(training_data.keys())
+        keys = random.sample(keys, len(keys)) if shuffle else keys
+        e0 = time.perf_counter()
+        for i in keys:
+            window = training_data[i]                       # [1,F,T] view
+            u_len = window.shape[-1]
+            audio_chunk = augmentation(window.expand(num_negatives, -1, -1), n_clean=1)   # [aug..., clean]
+            if frame_shuffle_args['time_dimension'] or frame_shuffle_args['freq_dimension']:
+                audio_chunk[:num_negatives] = frame_shuffle(audio_chunk[:num_negatives], **frame_shuffle_args)
+            if random_noise:
+                audio_chunk[:num_negatives] = add_random_noise(audio_chunk[:num_negatives], random_noise)
+            out = model(audio_signal=audio_chunk)
+            post = out['final_posteriors']                  # [2, T', C] log-probs
+            text, ids = _pseudo_targets(post[-1].detach(), blank, tokenizer, beam_search_fn, beams)
+            if verbose:
+                noisy = GreedyCTCDecoder(tokenizer=tokenizer, blank_id=blank)(post[0].detach())
+                print(f'Pseudo targets: {text}\nNoisy predictions: {noisy}\n\n--\n')
+            pseudo = torch.tensor(ids, dtype=torch.long).unsqueeze(0).to(device, non_blocking=True) \
+                .repeat(num_negatives, 1)
+            augmented_outs = post[:num_negatives]
+            N, B = augmented_outs.shape[1], augmented_outs.shape[0]
+            total_tokens_in_loss = N * B
+            loss = ctc_loss_fn(augmented_outs.transpose(0, 1), pseudo,
+                               torch.full((B,), N, dtype=torch.long, device=device),
+                               torch.full((B,), pseudo.shape[1], dtype=torch.long, device=device)) / total_tokens_in_loss
+            optimizer.zero_grad(set_to_none=True)
+            loss.backward()
+            optimizer.step()
+            if d.get('_record_steps', False):
+                step_log.append({'key': i, 'ids': ids, 'loss': float(loss.item())})
+            if online:
+                kept[i] = (post[-1].detach(), u_len)
+        tm.add('adapt', time.perf_counter() - e0)
+        if print_runtimes:
+            torch.cuda.synchronize(device)
+            print(f'Epoch runtime: {time.perf_counter() - e0}')
+
+    f0 = time.perf_counter()
+    if not online:
+        model.eval()
+        training_data, training_keys = prepare_chunks(spec_dev, seq_len, overlap)
+        starts = sorted(training_keys)
+        u_lens = [int(training_data[i].shape[-1]) for i in starts]
+        flat, used, offs, ds = None, 0, [], []
+        with torch.no_grad():
+            for i in starts:
+                lp = model(audio_signal=training_data[i])['final_posteriors'][0]
+                rows = int(lp.shape[0])
+                if flat is None:                            # full windows come first: size from the first T'
+                    flat = torch.empty((rows * len(starts), C), dtype=torch.float32, device=device)
+                if used + rows > flat.shape[0]:
+                    flat = torch.cat([flat[:used], torch.empty((rows * 2, C), dtype=torch.float32, device=device)], 0)
+                flat[used:used + rows] = lp
+                offs.append(used)
+                ds.append(rows)
+                used += rows
+        model.train()                                       # lib.py:612
+    else:
+        starts = sorted(kept.keys())
+        u_lens = [kept[i][1] for i in starts]
+        ds = [int(kept[i][0].shape[0]) for i in starts]
+        flat = torch.cat([kept[i][0] for i in starts], 0)
+        offs, o = [], 0
+        for n_ in ds:
+            offs.append(o)
+            o += n_
+    tm.add('final_pass', time.perf_counter() - f0)
+
+    s0 = time.perf_counter()
+    pos = window_positions(starts, u_lens, ds, overlap)
+    logits, path = stitch_flat(flat, offs, pos, ds, want_path=(output == 'greedy'))
+    tm.add('stitch', time.perf_counter() - s0)
+
+    if return_params:
+        updated_model_params = [p.clone().detach().cpu() for p in model.parameters()]
+    # reset model parameters (lib.py:636-637)
+    with torch.no_grad():
+        for p, p_orig, rg in zip(params, original, req_grad):
+            p.data = p_orig.data
+            p.requires_grad = rg
+
+    if output == 'numpy':
+        result = logits.cpu().numpy()
+    elif output == 'device':
+        result = logits
+    elif output == 'greedy':
+        from .greedy import collapse_path_device
+        result = collapse_path_device(path, blank)
+    else:
+        raise ValueError(f"unknown output mode {output!r}")
+    if print_runtimes:
+        torch.cuda.synchronize(device)
+        print('dae runtimes:', {k: round(v, 4) for k, v in tm.t.items()})
+    if d.get('_record_steps', False):
+        args.__dict__['_step_log'] = step_log
+    return result if not return_params else (result, updated_model_params)
+
+
+dynamic_eval = dynamic_eval_ctc_loss
+
+
+# ----------------------------------------------------------------------------- CLI surface
+def apply_args(parser, argv=None):
+    """lcasr/lib.py:1756-1787.  ``-kwargs key=value`` values are parsed with ast.literal_eval (the
+    reference eval()s them, :1778-1781); non-literals stay strings."""
+    parser.add_argument('-c', '--checkpoint', type=str, default='', help='path to checkpoint')
+    parser.add_argument('-split', '--split', type=str, default='test', help='test or dev split')
+    parser.add_argument('-seq', '--seq_len', type=int, default=16384, help='-1 to use setting from config in checkpoint file')
+    parser.add_argument('-o', '--overlap', type=int, default=14336, help='-1 to use setting from config in checkpoint file')
+    parser.add_argument('-nv', '--not_verbose', action='store_true', help='verbose')
+    parser.add_argument('-log', '--log', type=str, default='')
+    parser.add_argument('-ds', '--dont_shuffle', action='store_true', help='dont shuffle')
+    parser.add_argument('-epochs', '--epochs', type=int, default=1, help='epochs')
+    parser.add_argument('-dfa', '--disable_flash_attention', action='store_true', help='disable flash attention')
+    parser.add_argument('-beamsearch', '--beamsearch', action='store_true', help='use beam search')
+    parser.add_argument('-kwargs', '--kwargs', nargs='+', help='kwargs')
+    parser.add_argument('-awmc', '--awmc', action='store_true', help='Use AWMC instead of dynamic eval')
+    parser.add_argument('--consistency', '--consistency', action='store_true', help='Use consistency training')
+    parser.add_argument('--freeze_subsampling', action='store_true')
+    parser.add_argument('--freeze_all_but_last_block_and_head', action='store_true')
+    parser.add_argument('--train_subsampling_only', action='store_true')
+    args = parser.parse_args(argv)
+    if args.kwargs is None:
+        args.kwargs = []
+    for kwarg in args.kwargs:
+        key, value = kwarg.split('=', 1)
+        try:
+            args.__dict__[key] = ast.literal_eval(value)
+        except (ValueError, SyntaxError):
+            args.__dict__[key] = value
+        print(f'Overriding {key} to {value}')
+    args.shuffle = not args.dont_shuffle
+    args.verbose = not args.not_verbose
+    return args

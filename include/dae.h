@@ -56,6 +56,11 @@ int dae_greedy_collapse(const float* lp, int64_t sB, int64_t sT, int B, int T, i
                         const int32_t* lengths, int blank,
                         int32_t* path, int32_t* ids, int32_t* n_ids, void* stream);
 
+/* Collapse an already computed per-frame argmax path (e.g. dae_stitch's fused `path` output):
+ * same collapse as above without the argmax pass.  path [B,T] int32, ids [B,T], n_ids [B]. */
+int dae_collapse_path(const int32_t* path, int B, int T, const int32_t* lengths, int blank,
+                      int32_t* ids, int32_t* n_ids, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (3a) SpecAugment masking fused with the [augmented..., clean...] batch build.
  * replaces: lcasr.utils.augmentation.SpecAugment.__call__ + Tensor.repeat at

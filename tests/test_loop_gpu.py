@@ -1,0 +1,98 @@
+"""GPU: dae.lib.dynamic_eval (CUDA kernels) vs the CPU-style oracle loop, same toy model on the same
+device, same seeds and band draws.  Pseudo-label ids per step are bit-exact; losses and the stitched
+posteriors agree to fp32 tolerances (the two loops share the model's cuBLAS kernels)."""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from toy import TOY, TOY_CONFIG, RecordingTokenizer, ToyModel, toy_spec  # noqa: E402
+
+from oracle import greedy_oracle  # noqa: E402
+from oracle.ref_loop import dynamic_eval_reference, make_args  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_pair(cuda, online, **over):
+    from dae import lib
+    from dae.optim import MADGRAD
+    from dae.standin import SyntheticTokenizer
+    kw = dict(TOY["kwargs"], **over)
+    spec = toy_spec(TOY["spec_seed"], TOY["spec_n"])
+    outs = []
+    for which in ("oracle", "dae"):
+        tok = RecordingTokenizer(SyntheticTokenizer(vocab_size=TOY["C"] - 1, seed=0))
+        model = ToyModel(TOY["C"], seed=TOY["model_seed"]).to(cuda)
+        model.device = cuda
+        before = [p.detach().clone() for p in model.parameters()]
+        args = make_args(TOY_CONFIG, online=online, _record_steps=True, **kw)
+        random.seed(TOY["seed"])
+        torch.manual_seed(TOY["seed"])
+        if which == "oracle":
+            rec = []
+            logits = dynamic_eval_reference(args, model, spec, TOY["seq_len"], TOY["overlap"], tok, MADGRAD, record=rec)
+        else:
+            logits = lib.dynamic_eval(args, model, spec, TOY["seq_len"], TOY["overlap"], tok, use_tqdm=False,
+                                      optim=MADGRAD)
+            rec = args._step_log
+        assert all(torch.equal(a, b) for a, b in zip(before, model.parameters())), "parameters must be restored"
+        outs.append((logits, rec, tok.encoded))
+    return outs
+
+
+@pytest.mark.parametrize("online", [False, True])
+def test_dynamic_eval_matches_oracle_loop(cuda, online):
+    (lo, ro, eo), (ld, rd, ed) = _run_pair(cuda, online)
+    assert [r["key"] for r in ro] == [r["key"] for r in rd]           # same window order (shuffle RNG)
+    assert eo == ed                                                    # pseudo-label ids: bit-exact, every step
+    for a, b in zip(ro, rd):
+        assert abs(a["loss"] - b["loss"]) <= 1e-4 * abs(a["loss"])     # north_star CTC tolerance
+    assert lo.shape == ld.shape and ld.dtype == np.float32
+    np.testing.assert_allclose(np.exp(ld), np.exp(lo), rtol=2e-3, atol=1e-6)
+    assert (greedy_oracle.argmax_rows(ld) == greedy_oracle.argmax_rows(lo)).mean() > 0.995
+
+
+def test_dynamic_eval_epochs0_is_plain_inference(cuda):
+    (lo, ro, _), (ld, rd, _) = _run_pair(cuda, False, epochs=0)
+    assert ro == [] and rd == []
+    np.testing.assert_allclose(np.exp(ld), np.exp(lo), rtol=1e-4, atol=1e-7)
+
+
+def test_dynamic_eval_output_modes(cuda):
+    from dae import lib
+    from dae.optim import MADGRAD
+    from dae.standin import SyntheticTokenizer
+    tok = SyntheticTokenizer(vocab_size=TOY["C"] - 1, seed=0)
+    spec = toy_spec(3, 2000)
+    res = {}
+    for mode in ("numpy", "device", "greedy"):
+        model = ToyModel(TOY["C"], seed=1).to(cuda)
+        model.device = cuda
+        args = make_args(TOY_CONFIG, **dict(TOY["kwargs"], shuffle=False, epochs=1))
+        random.seed(0)
+        torch.manual_seed(0)
+        res[mode] = lib.dynamic_eval(args, model, spec, 1024, 512, tok, use_tqdm=False, optim=MADGRAD, output=mode)
+    assert isinstance(res["numpy"], np.ndarray) and res["device"].is_cuda
+    np.testing.assert_array_equal(res["numpy"], res["device"].cpu().numpy())
+    assert res["greedy"] == greedy_oracle.greedy_ids(res["numpy"], TOY["C"] - 1)
+    logits, params = lib.dynamic_eval(args, model, spec, 1024, 512, tok, use_tqdm=False, optim=MADGRAD, return_params=True)
+    assert len(params) == len(list(model.parameters())) and not params[0].is_cuda
+    assert any(not torch.equal(p.cpu(), q) for p, q in zip(model.parameters(), params))   # adapted copy differs
+
+
+def test_short_recording_single_window(cuda):
+    from dae import lib
+    from dae.optim import MADGRAD
+    from dae.standin import SyntheticTokenizer
+    tok = SyntheticTokenizer(vocab_size=TOY["C"] - 1, seed=0)
+    model = ToyModel(TOY["C"], seed=2).to(cuda)
+    model.device = cuda
+    args = make_args(TOY_CONFIG, **TOY["kwargs"])
+    out = lib.dynamic_eval(args, model, toy_spec(1, 600), 1024, 512, tok, use_tqdm=False, optim=MADGRAD)
+    assert out.shape == (75, TOY["C"])
+    np.testing.assert_allclose(np.exp(out).sum(-1), 1.0, rtol=1e-4)

@@ -88,8 +88,11 @@ def main():
         spec = torch.randn(1, 80, 120000, device="cuda")
         win = spec[:, :, 2048:2048 + 16384]
         aug = SpecAugment(n_freq_masks=6, freq_mask_param=34)
-        med, best = tm.time(lambda: aug(win, n_clean=1), args.iters)
+        bands = aug.draw(1, 80, 16384)
+        med, best = tm.time(lambda: aug(win, n_clean=1, bands=bands), args.iters)
         report("specaug_repeat", [80, 16384], 3 * 80 * 16384 * 4, med, best)
+        med, best = tm.time(lambda: aug(win, n_clean=1), args.iters)
+        report("specaug_repeat(+host band draw)", [80, 16384], 3 * 80 * 16384 * 4, med, best)
 
     if want("ctc"):
         for N in (1, 8, 64):

@@ -127,6 +127,27 @@ int dae_stitch(const float* lp, int C, const int64_t* win_off, const int64_t* wi
                const int64_t* win_len, int n_win, const int64_t* row_map, int64_t n_out,
                float* out, int32_t* path, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * (2) soft-DTW forward / backward on a pairwise cost matrix.
+ * replaces: _SoftDTWCUDA.forward/backward and the numba kernels compute_softdtw_cuda /
+ *           compute_softdtw_backward_cuda at lcasr_nemo/soft_dtw_cuda.py:33-111,114-174, and the CPU
+ *           kernels :184-239 the reference falls back to above 1024 frames (:312-314).
+ * D    [B,N,M] fp32 contiguous cost matrices
+ * R    [B,N,M] fp32: R[b,i,j] = D[b,i,j] + softmin_gamma(R[i-1,j-1], R[i-1,j], R[i,j-1]) with the
+ *      reference's borders (R[-1,-1] = 0, other border cells +inf); +inf where |i-j| > bandwidth > 0.
+ *      This is the interior R[:,1:N+1,1:M+1] of the reference's padded array.
+ * out  [B] = R[b,N-1,M-1] (the soft-DTW value, the reference's R[:, -2, -2])
+ * bwd: E [B,N,M] = gout[b] * dR[N-1,M-1]/dD  (the reference's grad_output * E[:,1:N+1,1:M+1]);
+ *      gout[b*gout_stride] is the upstream gradient of out[b].
+ * scratch: dae_softdtw_scratch_bytes() bytes, 256-byte aligned; zeroed by the call itself.
+ * ------------------------------------------------------------------------------------ */
+size_t dae_softdtw_scratch_bytes(int B, int N, int M);
+int dae_softdtw_fwd(const float* D, int B, int N, int M, float gamma, float bandwidth,
+                    float* R, float* out, void* scratch, size_t scratch_bytes, void* stream);
+int dae_softdtw_bwd(const float* D, const float* R, const float* gout, int64_t gout_stride,
+                    int B, int N, int M, float gamma, float bandwidth,
+                    float* E, void* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

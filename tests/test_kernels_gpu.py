@@ -158,12 +158,23 @@ def test_ctc_matches_fp64_oracle(cuda, T, N, C, Lmax):
         assert np.all(got[int(il[n]):, n] == 0)
 
 
+def _teacher_student(T, C, g, noise):
+    """[2,T,C] posteriors like the adapt step's batch: row 1 = clean teacher branch, row 0 = the same
+    frames seen through an augmentation (correlated, not identical)."""
+    teacher_logits = torch.randn(T, C, generator=g)
+    cls = torch.randint(0, C - 1, (T,), generator=g)
+    cls[torch.rand(T, generator=g) < 0.7] = C - 1
+    teacher_logits[torch.arange(T), cls] += 8
+    student_logits = teacher_logits + noise * torch.randn(T, C, generator=g)
+    return torch.stack([student_logits.log_softmax(-1), teacher_logits.log_softmax(-1)])
+
+
 def test_ctc_hot_path_shape_vs_torch(cuda):
     """cfg2 shape: lp is the non-contiguous view out[:1].transpose(0,1) of [2,2048,4096] (lib.py:570-575)."""
     from dae.ctc import CTCLoss
     T, C = 2048, 4096
     g = torch.Generator().manual_seed(0)
-    post = torch.stack([_peaky(T, C, C - 1, g, p_blank=0.7) for _ in range(2)]).to(cuda).requires_grad_()
+    post = _teacher_student(T, C, g, noise=1.0).to(cuda).requires_grad_()
     labels = greedy_oracle.greedy_ids(post[1].detach().cpu().numpy(), C - 1)
     tg = torch.tensor(labels, dtype=torch.long, device=cuda)[None]
     L = len(labels)
@@ -177,13 +188,35 @@ def test_ctc_hot_path_shape_vs_torch(cuda):
     ref_loss = torch.nn.CTCLoss(blank=C - 1, reduction="sum")(aug, tg, il, tl) / T
     ref_loss.backward()
     assert abs(loss.item() - ref_loss.item()) <= 1e-4 * abs(ref_loss.item())
-    assert torch.all(got[1] == 0)
-    # torch's own fp32 lattice is the looser side here (see tests/test_oracle_pins.py); compare to fp64 too
-    np.testing.assert_allclose(got[0].cpu().numpy(), post.grad[0].cpu().numpy(), atol=2e-2 / T, rtol=5e-2)
+    assert torch.all(got[1] == 0)                       # the clean copy gets no gradient
     nll, grad = ctc_oracle.ctc_loss_grad(post[:1].detach().transpose(0, 1).double().cpu().numpy(), [labels], [T], [L],
                                          C - 1, gout=1.0 / T)
-    _assert_ctc_grad_close(got[0].cpu().numpy(), grad[:, 0], post[0].detach().double().cpu().numpy(), 1.0 / T)
     assert abs(loss.item() * T - nll[0]) <= 1e-4 * nll[0]
+    _assert_ctc_grad_close(got[0].cpu().numpy(), grad[:, 0], post[0].detach().double().cpu().numpy(), 1.0 / T)
+    # torch's own fp32 CUDA lattice is the looser side: we must be at least as close to fp64 as it is
+    err_dae = np.abs(got[0].cpu().numpy() - grad[:, 0]).max()
+    err_torch = np.abs(post.grad[0].cpu().numpy() - grad[:, 0]).max()
+    assert err_dae <= err_torch + 1e-9
+
+
+def test_ctc_mismatched_labels_vs_fp64(cuda):
+    """Adversarial: labels unrelated to the posteriors, so the alignment runs through states ~2^-1000 below
+    the per-frame maximum.  fp32 log-space keeps ~1e-3 there (documented in DESIGN.md); torch fp32 is worse."""
+    from dae.ctc import CTCLoss
+    T, C, L = 1024, 512, 300
+    g = torch.Generator().manual_seed(2)
+    post = _teacher_student(T, C, g, noise=0.0)[1]
+    tgt = torch.randint(0, C - 1, (1, L), generator=g)
+    x = post[:, None].to(cuda).requires_grad_()
+    loss = CTCLoss(blank=C - 1, reduction="sum")(x, tgt.to(cuda), [T], [L])
+    loss.backward()
+    nll, grad = ctc_oracle.ctc_loss_grad(post[:, None].double().numpy(), tgt.numpy(), [T], [L], C - 1)
+    assert abs(loss.item() - nll[0]) <= 1e-5 * nll[0]
+    got = x.grad.cpu().numpy()
+    np.testing.assert_allclose(got, grad, rtol=5e-3, atol=5e-3 * np.exp(post.numpy())[:, None] + 1e-9)
+    y = post[:, None].to(cuda).requires_grad_()
+    torch.nn.CTCLoss(blank=C - 1, reduction="sum")(y, tgt.to(cuda), [T], [L]).backward()
+    assert np.abs(got - grad).max() <= np.abs(y.grad.cpu().numpy() - grad).max() + 1e-9
 
 
 def test_ctc_reductions_and_infeasible(cuda):

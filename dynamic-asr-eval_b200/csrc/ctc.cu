@@ -262,23 +262,37 @@ ctc_lattice_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, 
     }
     __syncthreads();                                   // "start": consumers may run step 0
 
-    double off_acc = 0.0;
+    double off_acc = 0.0;                              // A_t: total offset removed up to step t
+    double a_prev = 0.0;                               // A_{t-1}
+    double m_prev2 = 0.0;                              // true maximum M_{t-2} = max~_{t-2} + A_{t-2}
+    bool have_prev2 = false;
     int wslot = 1 % R;                                 // ring slot of step t+1
     uint32_t wphase = (1 / R) & 1;
     int64_t tt_next = t_first + (dir ? -1 : 1);        // actual frame index of step t+1
     for (int t = 0; t < Tn; ++t) {
       if (t + 1 < Tn) {
         mbar_wait(&full[wslot], wphase);
-        // centring constant of step t+1: maximum over the lattice at step t-1 (lag 2)
+        // Centring constant of step t+1.  The newest maxima available are those of step t-1 (lag 2), so
+        // extrapolate the per-step drift: aim A_{t+1} at M_{t-1} + 2*(M_{t-1} - M_{t-2}).  Any value is
+        // valid (it is only a shift); a good one keeps the stored lattice near 0 where fp32 is densest.
         float c = 0.0f;
         if (t >= 1) {
           int v = (lane < n_cwarps) ? wmx[((t - 1) & 3) * 32 + lane] : f2ord(-CUDART_INF_F);
           v = __reduce_max_sync(0xffffffffu, v);
-          c = ord2f(v);
-          if (c == -CUDART_INF_F) c = 0.0f;
+          const float mt = ord2f(v);
+          if (mt != -CUDART_INF_F) {
+            const double m1 = (double)mt + a_prev;
+            const double drift = have_prev2 ? (m1 - m_prev2) : 0.0;
+            c = (float)(m1 + 2.0 * drift - off_acc);
+            m_prev2 = m1;
+            have_prev2 = true;
+          } else {
+            have_prev2 = false;
+          }
         }
+        a_prev = off_acc;
+        off_acc += (double)c;                            // warp-uniform
         if (lane == 0) {
-          off_acc += (double)c;
           offs[tt_next] = off_acc;
           const float xbl = reinterpret_cast<const float*>(rows + (size_t)wslot * lay.row_stride)[blank];
           cxs[(t + 1) & 3] = make_float2(c, fmaf(xbl, kLog2e, -c));
@@ -513,7 +527,6 @@ extern "C" int dae_ctc_lattice(const float* lp, int64_t sT, int64_t sN, int T, i
   constexpr int kMaxConsumers = kLatThreads - 32;        // one warp is the TMA producer
   int P = (pairs + kMaxConsumers - 1) / kMaxConsumers;
   P = P <= 1 ? 1 : (P <= 2 ? 2 : 4);
-  if (pairs > 320 && P == 1) P = 2;                      // fewer, fatter warps: less issue pressure per step
   if (const char* e = getenv("DAE_CTC_PAIRS")) {         // tuning override (1, 2 or 4 pairs per thread)
     const int q = atoi(e);
     if ((q == 1 || q == 2 || q == 4) && (pairs + q - 1) / q <= kMaxConsumers) P = q;

@@ -213,7 +213,8 @@ def test_ctc_mismatched_labels_vs_fp64(cuda):
     nll, grad = ctc_oracle.ctc_loss_grad(post[:, None].double().numpy(), tgt.numpy(), [T], [L], C - 1)
     assert abs(loss.item() - nll[0]) <= 1e-5 * nll[0]
     got = x.grad.cpu().numpy()
-    np.testing.assert_allclose(got, grad, rtol=5e-3, atol=5e-3 * np.exp(post.numpy())[:, None] + 1e-9)
+    tol = 5e-3 * np.abs(grad) + 5e-3 * np.exp(post.numpy())[:, None] + 1e-9
+    assert (np.abs(got - grad) <= tol).all(), float((np.abs(got - grad) / tol).max())
     y = post[:, None].to(cuda).requires_grad_()
     torch.nn.CTCLoss(blank=C - 1, reduction="sum")(y, tgt.to(cuda), [T], [L]).backward()
     assert np.abs(got - grad).max() <= np.abs(y.grad.cpu().numpy() - grad).max() + 1e-9
@@ -234,7 +235,9 @@ def test_ctc_reductions_and_infeasible(cuda):
 
 
 def test_ctc_large_magnitude_precision(cuda):
-    """|log-likelihood| ~ 2e4: the centred lattice must stay within 1e-4 of fp64 where torch fp32 drifts."""
+    """Random logits, |log-likelihood| ~ 1e4 and the alignment far below the per-frame maximum: the centred
+    fp32 lattice keeps the loss to 1e-5 and the gradient to ~1e-3 of its scale (DESIGN.md "CTC accuracy");
+    torch's uncentred fp32 kernel is an order of magnitude further from fp64."""
     from dae.ctc import CTCLoss
     T, N, C, L = 2048, 1, 512, 300
     lp, tg, il, tl, blank = _ctc_case(T, N, C, L, seed=1, ragged=False)
@@ -244,7 +247,13 @@ def test_ctc_large_magnitude_precision(cuda):
     nll, grad = ctc_oracle.ctc_loss_grad(lp.double().numpy(), tg.numpy(), il.numpy(), tl.numpy(), blank)
     assert nll[0] > 5000
     assert abs(loss.item() - nll[0]) <= 1e-5 * nll[0]
-    _assert_ctc_grad_close(x.grad.cpu().numpy(), grad, lp.double().numpy(), 1.0)
+    err = np.abs(x.grad.cpu().numpy() - grad).max()
+    assert err <= 3e-3 * np.abs(grad).max()
+    y = lp.to(cuda).requires_grad_()
+    torch.nn.CTCLoss(blank=blank, reduction="sum")(y, tg.to(cuda), il, tl).backward()
+    err_torch = np.abs(y.grad.cpu().numpy() - grad).max()
+    print(f"max |grad - fp64|: dae {err:.2e}, torch.cuda fp32 {err_torch:.2e}")
+    assert err < err_torch
 
 
 # ---------------------------------------------------------------- stitch

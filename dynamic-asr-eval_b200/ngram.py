@@ -1,0 +1,181 @@
+"""Token-level back-off n-gram language model held as a flat trie in HBM.
+
+This replaces the Transformer LM behind ``ctc_beam_search.LanguageModel`` (lcasr/ctc_beam_search.py:45-87,
+built by lcasr/lib.py:37-72) with the ARPA n-gram the north star asks for.  The reference has no n-gram
+code of its own (pyctcdecode/kenlm are absent and unpinned), so the semantics are defined
+here and restated independently in oracle/beam_oracle.py:
+
+  score(h, w), h = last (order-1) tokens of the LM sequence (bos included):
+      acc = 0
+      for ctx in (h, h[1:], ..., ()):            # longest context first
+          if ctx+(w,) is an n-gram: return acc + logp(ctx+(w,))
+          acc = acc + backoff(ctx)               # 0 when ctx has no entry
+      return acc + unk_logp
+  all values are natural-log fp32 (ARPA log10 * ln 10, rounded once), all adds fp32 in that order.
+
+Device layout (one node per n-gram, root = node 0, nodes ordered by (depth, parent, token) so the
+children of a node are one sorted run): tok[n], logp[n], bo[n], fail[n] (node of the longest proper
+suffix), cb[n]..cb[n+1] (child run), depth[n].  A beam's LM state is the node of its longest context
+suffix present in the trie; scoring walks fail links with one binary search per level.
+"""
+import gzip
+import math
+import random
+
+import numpy as np
+import torch
+
+LN10 = math.log(10.0)
+
+
+def write_synthetic_arpa(path, vocab_size, order=4, counts=(None, 2000, 4000, 4000), seed=4, bos_id=0):
+    """Write a random but well-formed ARPA file (prefix- and suffix-closed) over token ids 1..vocab_size-1
+    (words are decimal ids, ``<s>`` is the bos token).  counts[k-1] = number of k-grams (None = all unigrams)."""
+    rng = random.Random(seed)
+    toks = list(range(1, vocab_size))
+    levels = []
+    uni = {(bos_id,): (-99.0, rng.uniform(-1.0, -0.05))}
+    for t in toks:
+        uni[(t,)] = (rng.uniform(-4.0, -0.5), rng.uniform(-1.0, -0.05))
+    levels.append(uni)
+    for k in range(2, order + 1):
+        prev = levels[-1]
+        prev_keys = list(prev.keys())
+        by_prefix = {}
+        for g in prev_keys:
+            by_prefix.setdefault(g[:-1], []).append(g)
+        want = counts[k - 1] if counts[k - 1] is not None else len(prev_keys)
+        cur, tries = {}, 0
+        while len(cur) < want and tries < want * 50:
+            tries += 1
+            g = rng.choice(prev_keys)
+            cands = by_prefix.get(g[1:], None)          # (k-1)-grams starting with g's suffix
+            if not cands:
+                continue
+            h = rng.choice(cands)
+            ng = g + (h[-1],)
+            if ng[-1] == bos_id or ng in cur:
+                continue
+            cur[ng] = (rng.uniform(-3.0, -0.05), rng.uniform(-1.0, -0.02) if k < order else None)
+        levels.append(cur)
+    name = lambda t: "<s>" if t == bos_id else str(t)
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "wt") as f:
+        f.write("\\data\\\n")
+        for k, lv in enumerate(levels, 1):
+            f.write(f"ngram {k}={len(lv)}\n")
+        for k, lv in enumerate(levels, 1):
+            f.write(f"\n\\{k}-grams:\n")
+            for ng in sorted(lv):
+                lp, bo = lv[ng]
+                words = " ".join(name(t) for t in ng)
+                f.write(f"{lp:.6f}\t{words}" + (f"\t{bo:.6f}\n" if bo is not None else "\n"))
+        f.write("\n\\end\\\n")
+    return sum(len(lv) for lv in levels)
+
+
+def read_arpa(path, word_to_id=None, bos_id=0):
+    """-> (order, {tuple_of_ids: (logp10, backoff10 or None)}).  Unknown words are skipped."""
+    def default_map(w):
+        if w == "<s>":
+            return bos_id
+        if w in ("</s>", "<unk>"):
+            return None
+        try:
+            return int(w)
+        except ValueError:
+            return None
+    wmap = word_to_id or default_map
+    grams, order, cur = {}, 0, 0
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "rt") as f:
+        for line in f:
+            line = line.strip()
+            if not line or line.startswith("ngram ") or line in ("\\data\\", "\\end\\"):
+                continue
+            if line.startswith("\\") and line.endswith("-grams:"):
+                cur = int(line[1:line.index("-")])
+                order = max(order, cur)
+                continue
+            parts = line.split("\t") if "\t" in line else line.split()
+            if "\t" in line:
+                lp, words = float(parts[0]), parts[1].split()
+                bo = float(parts[2]) if len(parts) > 2 else None
+            else:
+                lp, words = float(parts[0]), parts[1:1 + cur]
+                bo = float(parts[1 + cur]) if len(parts) > 1 + cur else None
+            ids = tuple(wmap(w) for w in words)
+            if any(i is None for i in ids):
+                continue
+            grams[ids] = (lp, bo)
+    return order, grams
+
+
+class NGramLM:
+    """Flat-trie n-gram LM.  ``language_model=`` argument of dae.ctc_beam_search.BeamSearch."""
+
+    def __init__(self, grams, order, vocab_size, bos_id=0, unk_logprob10=-10.0):
+        self.order, self.vocab_size, self.bos_id = int(order), int(vocab_size), int(bos_id)
+        self.unk_lp = np.float32(unk_logprob10 * LN10)
+        by_depth = [[] for _ in range(order + 1)]
+        for ng in grams:
+            if 1 <= len(ng) <= order:
+                by_depth[len(ng)].append(ng)
+        ids = {(): 0}
+        tok, logp, bo, depth, parent = [0], [0.0], [0.0], [0], [0]
+        for k in range(1, order + 1):
+            # parents already numbered; order this level by (parent id, token): children of a node are one run
+            level = [ng for ng in by_depth[k] if ng[:-1] in ids]
+            level.sort(key=lambda ng: (ids[ng[:-1]], ng[-1]))
+            for ng in level:
+                lp10, bo10 = grams[ng]
+                ids[ng] = len(tok)
+                tok.append(ng[-1])
+                logp.append(lp10 * LN10)
+                bo.append((bo10 or 0.0) * LN10)
+                depth.append(k)
+                parent.append(ids[ng[:-1]])
+        n = len(tok)
+        par = np.asarray(parent, dtype=np.int64)
+        cnt = np.bincount(par[1:], minlength=n)
+        cb = (1 + np.concatenate(([0], np.cumsum(cnt)))).astype(np.int32)   # root's children start at node 1
+        fail = np.zeros(n, dtype=np.int32)
+        for ng, i in ids.items():
+            for s in range(1, len(ng)):
+                j = ids.get(ng[s:])
+                if j is not None:
+                    fail[i] = j
+                    break
+        self.tok = np.asarray(tok, dtype=np.int32)
+        self.logp = np.asarray(logp, dtype=np.float64).astype(np.float32)
+        self.bo = np.asarray(bo, dtype=np.float64).astype(np.float32)
+        self.depth = np.asarray(depth, dtype=np.int32)
+        self.fail, self.cb, self.n_nodes = fail, cb, n
+        self._ids = ids
+        self._dev = {}
+
+    @classmethod
+    def from_arpa(cls, path, vocab_size, bos_id=0, word_to_id=None, unk_logprob10=-10.0):
+        order, grams = read_arpa(path, word_to_id, bos_id)
+        return cls(grams, order, vocab_size, bos_id, unk_logprob10)
+
+    def nbytes(self):
+        return sum(a.nbytes for a in (self.tok, self.logp, self.bo, self.depth, self.fail, self.cb))
+
+    def device_arrays(self, device):
+        """Upload once per device; returns dict of CUDA tensors (the trie stays resident in HBM)."""
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = {k: torch.from_numpy(getattr(self, k)).to(device)
+                              for k in ("tok", "logp", "bo", "depth", "fail", "cb")}
+        return self._dev[key]
+
+    # host-side state helpers (index arithmetic only; scoring happens on the device)
+    def state_of(self, history):
+        """Trie node of the longest suffix of ``history`` (at most order-1 tokens) that is a node."""
+        h = tuple(history)[-(self.order - 1):] if self.order > 1 else ()
+        for s in range(len(h) + 1):
+            j = self._ids.get(h[s:])
+            if j is not None:
+                return j
+        return 0

@@ -148,6 +148,36 @@ int dae_softdtw_bwd(const float* D, const float* R, const float* gout, int64_t g
                     int B, int N, int M, float gamma, float bandwidth,
                     float* E, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * (4) CTC prefix beam search with shallow n-gram LM fusion, one CTA per segment.
+ * replaces: BeamSearch.run_search / step / merge / prune at lcasr/ctc_beam_search.py:152-319 and the
+ *           per-frame LM calls of LanguageModel.__call__ (:77-87); the LM is a back-off n-gram trie in
+ *           HBM (layout: dae/ngram.py) instead of the Transformer LM of lcasr/lib.py:37-72.
+ * lp           [total_T, C] fp32 log-probs, row stride C; blank must be C-1 (the class assumes
+ *              blank_id == vocab_size, lib.py:64)
+ * seg_offsets  [n_seg+1] int32 (device): segment g = rows seg_offsets[g] .. seg_offsets[g+1]
+ * lm_*         flat trie arrays on the device (tok/logp/bo/fail/depth [lm_nodes], cb [lm_nodes+1])
+ * scratch      dae_beam_scratch_bytes(n_seg, arena_cap) bytes, 256-aligned; holds the beams and the
+ *              backpointer arena (arena_cap new-token entries per segment) and persists between
+ *              calls, so a search can be advanced t_count frames at a time (BeamSearch.step()).
+ *              t_begin == 0 (re)initialises the search; otherwise it resumes from the stored position.
+ * finalize     non-zero: write the n_best best beams of every segment:
+ *              out_score/out_len/out_flag [n_seg, n_best], out_tok/out_time [n_seg, n_best, out_cap]
+ *              (token ids and their start frames), out_n [n_seg, 2] = (number of live beams, error code:
+ *              0, DAE_E_TOOBIG = more than 4096 candidates in one frame, DAE_E_SCRATCH = arena full).
+ * ------------------------------------------------------------------------------------ */
+size_t dae_beam_scratch_bytes(int n_seg, int arena_cap);
+int dae_beam_search(const float* lp, const int32_t* seg_offsets, int n_seg, int C, int blank,
+                    int beam_width, float alpha, float beta, float top_am_threshold,
+                    float prune_less_than_val, int has_prune, float blank_penalty, float repetition_penalty,
+                    const int32_t* lm_tok, const float* lm_logp, const float* lm_bo, const int32_t* lm_fail,
+                    const int32_t* lm_cb, const int32_t* lm_depth, int lm_nodes, int lm_order,
+                    int lm_bos_state, float lm_unk_lp,
+                    void* scratch, size_t scratch_bytes, int arena_cap,
+                    int t_begin, int t_count, int finalize, int n_best, int out_cap,
+                    float* out_score, int32_t* out_len, int32_t* out_flag, int32_t* out_tok,
+                    int32_t* out_time, int32_t* out_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -326,6 +326,175 @@ def dynamic_eval_ctc_loss(
 dynamic_eval = dynamic_eval_ctc_loss
 
 
+class _EMA:
+    """On-device exponential moving average of parameters with torch_ema's call surface
+    (``update()``, ``average_parameters()`` context manager), as AWMC uses it (lcasr/lib.py:243-246,283-291)."""
+
+    def __init__(self, parameters, decay):
+        self.params = list(parameters)
+        self.decay = float(decay)
+        self.shadow = [p.detach().clone() for p in self.params]
+        self.num_updates = 0
+
+    @torch.no_grad()
+    def update(self):
+        self.num_updates += 1
+        decay = min(self.decay, (1 + self.num_updates) / (10 + self.num_updates))   # torch_ema's warm-up
+        if decay >= 1.0:
+            return
+        torch._foreach_lerp_(self.shadow, [p.detach() for p in self.params], 1.0 - decay)
+
+    def average_parameters(self):
+        ema = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                self_inner.saved = [p.detach().clone() for p in ema.params]
+                with torch.no_grad():
+                    for p, s in zip(ema.params, ema.shadow):
+                        p.data.copy_(s)
+                return ema.shadow
+
+            def __exit__(self_inner, *exc):
+                with torch.no_grad():
+                    for p, s in zip(ema.params, self_inner.saved):
+                        p.data.copy_(s)
+                return False
+        return _Ctx()
+
+
+def AWMC(
+        args,
+        model: nn.Module,
+        spec: torch.Tensor,
+        seq_len: int,
+        overlap: int,
+        tokenizer,
+        use_tqdm: bool = True,
+        optim=MADGRAD,
+        optimizer_state: dict = None,
+        beam_search_fn: Callable = None,
+        return_params: bool = False,
+        output: str = "numpy",
+):
+    """Anchor/leader EMA-teacher baseline, lcasr/lib.py:206-376, on the dae kernels: greedy pseudo-labels of
+    the anchor (first epoch) and leader models on the device, CTC on the N=2 ragged label bank, per-window
+    final posterior, overlap stitch."""
+    assert beam_search_fn is None, 'Beam search function not implemented for AWMC'
+    device = model.device
+    if torch.device(device).type != "cuda":
+        raise _C.DaeError("dae.lib.AWMC needs the model on a CUDA device: there is no CPU path")
+    d = args.__dict__
+    spec_augment_config = get_specaugment_config_from_args(args)
+    lr_args = get_lr_args_from_args(args)
+    frame_shuffle_args = get_frame_shuffle_config_from_args(args)
+    spec_n = spec.shape[-1]
+    downsampling_factor = args.config['model']['subsampling_factor']
+    seq_len = seq_len if seq_len != -1 else args.config['audio_chunking']['size']
+    params = list(model.parameters())
+    original = [p.detach().clone() for p in params]
+    req_grad = [p.requires_grad for p in params]
+    model = _freeze(model, args)
+    model.train()                                           # lib.py:242
+    ema_leader = _EMA(model.parameters(), decay=d.get('ema_decay', 0.999))
+    ema_leader.update()
+    ema_anchor = _EMA(model.parameters(), decay=1.0)
+    ema_anchor.update()
+    blank = model.decoder.num_classes - 1
+    ctc_loss_fn = CTCLoss(blank=blank, reduction='sum')
+    optimizer = optim([p for p in model.parameters() if p.requires_grad], **lr_args)
+    if optimizer_state is not None:
+        optimizer.load_state_dict(optimizer_state)
+    augmentation = SpecAugment(**spec_augment_config)
+    if seq_len > spec_n:
+        seq_len, overlap = spec_n, 0
+    else:
+        overlap = overlap if overlap != -1 else args.config['audio_chunking']['overlap']
+    assert args.config['training'].get("max_seq_len", 0) == 0, 'caching is not used anymore'
+    assert overlap / downsampling_factor == overlap // downsampling_factor
+    epochs = d.get('epochs', 1)
+    spec_dev = spec.to(device, non_blocking=True).float() if not spec.is_cuda else spec.float()
+    training_data, training_keys = prepare_chunks(spec_dev, seq_len, overlap)
+    C = model.decoder.num_classes
+
+    def labels_of(lp):
+        _, ids, n = greedy_ids_device(lp, blank)
+        text = tokenizer.decode(ids[0, :int(n[0].item())].tolist())
+        return torch.tensor(tokenizer.encode(text), dtype=torch.long, device=device)
+
+    kept = {}
+    model.eval()                                            # lib.py:276
+    for i in training_keys:
+        label_bank = [None, None]
+        for j in range(epochs):
+            audio_chunk = training_data[i]
+            if j == 0:
+                with ema_anchor.average_parameters(), torch.no_grad():
+                    label_bank[0] = labels_of(model(audio_signal=audio_chunk)['final_posteriors'][-1])
+            with ema_leader.average_parameters(), torch.no_grad():
+                label_bank[1] = labels_of(model(audio_signal=audio_chunk)['final_posteriors'][-1])
+            noisy = augmentation(audio_chunk)
+            noisy = frame_shuffle(noisy, **frame_shuffle_args)
+            out = model(audio_signal=noisy)
+            post = out['final_posteriors']
+            labels = [el for el in label_bank if el.shape[0] > 0]
+            if len(labels) == 0:
+                labels = [torch.zeros(0, dtype=torch.long, device=device)]
+            lens = torch.tensor([el.shape[0] for el in labels], dtype=torch.long, device=device)
+            padded = torch.nn.utils.rnn.pad_sequence(labels, batch_first=True, padding_value=0)
+            N, B = post.shape[1], post.shape[0]
+            total_tokens_in_loss = N * B * 2
+            loss = ctc_loss_fn(post.repeat(lens.shape[0], 1, 1).transpose(0, 1), padded,
+                               torch.full((lens.shape[0],), N, dtype=torch.long, device=device), lens) / total_tokens_in_loss
+            optimizer.zero_grad(set_to_none=True)
+            loss.backward()
+            optimizer.step()
+            ema_leader.update()
+            if j == epochs - 1:
+                with torch.no_grad():
+                    kept[i] = (model(audio_signal=training_data[i])['final_posteriors'][0], int(audio_chunk.shape[-1]))
+    starts = sorted(kept.keys())
+    u_lens = [kept[i][1] for i in starts]
+    ds = [int(kept[i][0].shape[0]) for i in starts]
+    flat = torch.cat([kept[i][0] for i in starts], 0) if len(starts) > 1 else kept[starts[0]][0].contiguous()
+    offs, o = [], 0
+    for n_ in ds:
+        offs.append(o)
+        o += n_
+    logits, path = stitch_flat(flat, offs, window_positions(starts, u_lens, ds, overlap), ds,
+                               want_path=(output == 'greedy'))
+    if return_params:
+        updated_model_params = [p.clone().detach().cpu() for p in model.parameters()]
+    with torch.no_grad():
+        for p, p_orig, rg in zip(params, original, req_grad):
+            p.data = p_orig.data
+            p.requires_grad = rg
+    if output == 'numpy':
+        result = logits.cpu().numpy()
+    elif output == 'device':
+        result = logits
+    else:
+        from .greedy import collapse_path_device
+        result = collapse_path_device(path, blank)
+    return result if not return_params else (result, updated_model_params)
+
+
+def load_beamsearch(path: str, alpha: float = 0.45, beta: float = 1.53, prune_less_than_val: float = 3.17,
+                    top_am_threshold: float = -6, tokenizer=None, vocab_size=None, bos_id=None):
+    """lcasr/lib.py:37-72 with the LM checkpoint replaced by an ARPA n-gram file: returns
+    ``partial(BeamSearch, language_model=..., tokenizer=..., blank_id=vocab_size, alpha=..., ...)``."""
+    from . import ctc_beam_search as beam_search
+    from .ngram import NGramLM
+    if tokenizer is None:
+        from .standin import SyntheticTokenizer
+        tokenizer = SyntheticTokenizer()
+    V = vocab_size or tokenizer.vocab_size()
+    language_model = NGramLM.from_arpa(path, V, bos_id=tokenizer.bos_id() if bos_id is None else bos_id)
+    return partial(beam_search.BeamSearch, language_model=language_model, tokenizer=tokenizer, blank_id=V,
+                   alpha=alpha, beta=beta, debug=False, prune_less_than_val=prune_less_than_val,
+                   top_am_threshold=top_am_threshold, max_cache_length=128)
+
+
 # ----------------------------------------------------------------------------- CLI surface
 def apply_args(parser, argv=None):
     """lcasr/lib.py:1756-1787.  ``-kwargs key=value`` values are parsed with ast.literal_eval (the

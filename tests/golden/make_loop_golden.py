@@ -56,7 +56,8 @@ def install_stubs():
     if "matplotlib" not in sys.modules:
         stub("matplotlib", pyplot=types.SimpleNamespace())
         stub("matplotlib.pyplot")
-    stub("torch_ema", ExponentialMovingAverage=object)
+    from oracle.ref_loop import OracleEMA
+    stub("torch_ema", ExponentialMovingAverage=OracleEMA)
     stub("lcasr.utils.lm_tools", add_eos=None, token_lens_to_mask=None, mark_padding=None)
     stub("lcasr.components")
     stub("lcasr.components.batchrenorm", BatchRenorm1d=object)
@@ -92,6 +93,19 @@ def main():
         out[f"ids_len_{tag}"] = np.array([len(e) for e in tok.encoded], dtype=np.int64)
         out[f"min_margin_{tag}"] = np.float64(model.min_margin)
         print(tag, logits.shape, len(tok.encoded), [len(e) for e in tok.encoded], 'min top-2 margin', model.min_margin)
+    # AWMC baseline (lib.py:206-376) through the same stubs
+    tok = RecordingTokenizer(SyntheticTokenizer(vocab_size=TOY["C"] - 1, seed=0))
+    model = ToyModel(TOY["C"], seed=TOY["model_seed"])
+    args = make_args(TOY_CONFIG, **dict(TOY["kwargs"], ema_decay=0.9))
+    random.seed(TOY["seed"])
+    torch.manual_seed(TOY["seed"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        logits = ref_lib.AWMC(args, model, toy_spec(TOY["spec_seed"], TOY["spec_n"]), TOY["seq_len"], TOY["overlap"], tok,
+                              use_tqdm=False, optim=MADGRAD)
+    out["logits_awmc"] = logits.astype(np.float32)
+    out["ids_flat_awmc"] = np.array([i for e in tok.encoded for i in e], dtype=np.int64)
+    out["ids_len_awmc"] = np.array([len(e) for e in tok.encoded], dtype=np.int64)
+    print("awmc", logits.shape, len(tok.encoded))
     # chunk index vectors from the reference's prepare_chunks at the BASELINE window settings
     for spec_n in (6000, 120000, 360000, 415990):
         td, keys = ref_lib.prepare_chunks(torch.zeros(1, 1, spec_n), 16384, 14336)

@@ -96,3 +96,60 @@ def test_short_recording_single_window(cuda):
     out = lib.dynamic_eval(args, model, toy_spec(1, 600), 1024, 512, tok, use_tqdm=False, optim=MADGRAD)
     assert out.shape == (75, TOY["C"])
     np.testing.assert_allclose(np.exp(out).sum(-1), 1.0, rtol=1e-4)
+
+
+def test_awmc_matches_oracle_loop(cuda):
+    from dae import lib
+    from dae.optim import MADGRAD
+    from dae.standin import SyntheticTokenizer
+    from oracle.ref_loop import awmc_reference
+    spec = toy_spec(TOY["spec_seed"], TOY["spec_n"])
+    outs = []
+    for which in ("oracle", "dae"):
+        tok = RecordingTokenizer(SyntheticTokenizer(vocab_size=TOY["C"] - 1, seed=0))
+        model = ToyModel(TOY["C"], seed=TOY["model_seed"]).to(cuda)
+        model.device = cuda
+        before = [p.detach().clone() for p in model.parameters()]
+        args = make_args(TOY_CONFIG, **dict(TOY["kwargs"], ema_decay=0.9))
+        random.seed(TOY["seed"])
+        torch.manual_seed(TOY["seed"])
+        if which == "oracle":
+            logits = awmc_reference(args, model, spec, TOY["seq_len"], TOY["overlap"], tok, MADGRAD)
+        else:
+            logits = lib.AWMC(args, model, spec, TOY["seq_len"], TOY["overlap"], tok, use_tqdm=False, optim=MADGRAD)
+        assert all(torch.equal(a, b) for a, b in zip(before, model.parameters()))
+        outs.append((logits, tok.encoded))
+    (lo, eo), (ld, ed) = outs
+    assert eo == ed                                                    # anchor/leader label banks: bit-exact
+    np.testing.assert_allclose(np.exp(ld), np.exp(lo), rtol=2e-3, atol=1e-6)
+
+
+def test_run_dynamic_eval_full_main_and_beamsearch(cuda, tmp_path):
+    """Entry point end to end on synthetic recordings: greedy path, pickle schema, then the LM beam-search path."""
+    import pickle
+    from types import SimpleNamespace
+    from dae import lib, run_dynamic_eval_full as r
+    from dae.ngram import write_synthetic_arpa
+    from dae.standin import SyntheticTokenizer, synthetic_recordings
+    V = TOY["C"] - 1
+    tok = SyntheticTokenizer(vocab_size=V, seed=0)
+    data = synthetic_recordings("tedlium", tokenizer=tok, scale=0.004)[:3]           # a few seconds each
+    model = ToyModel(TOY["C"], seed=TOY["model_seed"])
+    save = str(tmp_path / "res.pkl")
+    args = SimpleNamespace(split="test", dataset="tedlium", repeats=1, save_path=save, log="", checkpoint="toy",
+                           seq_len=1024, overlap=512, awmc=False, consistency=False, config=TOY_CONFIG,
+                           **dict(TOY["kwargs"], epochs=1))
+    wer = r.main(args, model=model, tokenizer=tok, data=data, normalize=lambda s: s)
+    assert wer > 0 and np.isfinite(wer)
+    saved = pickle.load(open(save.replace(".pkl", "_1.pkl"), "rb"))
+    assert set(saved) >= {"wer", "words", "ins_rate", "del_rate", "sub_rate", "model_output", "gold", "elapsed_times",
+                          "args_dict", "repeat"}
+    assert saved["wer"] == wer and len(saved["model_output"]) == 3
+    assert abs(saved["ins_rate"] + saved["del_rate"] + saved["sub_rate"] - wer) < 1e-12
+    # beam-search path (run_dynamic_eval_full.py:56-65,101-104): n-gram LM from an ARPA file
+    arpa = str(tmp_path / "lm.arpa")
+    write_synthetic_arpa(arpa, V, order=3, counts=(None, 400, 600), seed=2)
+    bs = lib.load_beamsearch(arpa, tokenizer=tok)
+    args.lm_eval_beams, args.lm_tta_beams, args.save_path = 5, 3, ""
+    wer2 = r.main(args, model=model, tokenizer=tok, data=data[:1], normalize=lambda s: s, beamsearch=bs)
+    assert np.isfinite(wer2)

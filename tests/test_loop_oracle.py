@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from toy import TOY, TOY_CONFIG, RecordingTokenizer, ToyModel, toy_spec  # noqa: E402
 
 from oracle import stitch_oracle  # noqa: E402
-from oracle.ref_loop import dynamic_eval_reference, make_args  # noqa: E402
+from oracle.ref_loop import awmc_reference, dynamic_eval_reference, make_args  # noqa: E402
 
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loop_toy.npz"))
 
@@ -51,3 +51,22 @@ def test_product_prepare_chunks_matches_golden():
     for spec_n in (6000, 120000, 415990):
         td, keys = prepare_chunks(torch.zeros(1, 1, spec_n), 16384, 14336)
         assert [[k, td[k].shape[-1]] for k in keys] == GOLD[f"chunks_{spec_n}"].tolist()
+
+
+def test_oracle_awmc_matches_reference_golden():
+    from dae.optim import MADGRAD
+    from dae.standin import SyntheticTokenizer
+    tok = RecordingTokenizer(SyntheticTokenizer(vocab_size=TOY["C"] - 1, seed=0))
+    model = ToyModel(TOY["C"], seed=TOY["model_seed"])
+    before = [p.detach().clone() for p in model.parameters()]
+    args = make_args(TOY_CONFIG, **dict(TOY["kwargs"], ema_decay=0.9))
+    random.seed(TOY["seed"])
+    torch.manual_seed(TOY["seed"])
+    logits = awmc_reference(args, model, toy_spec(TOY["spec_seed"], TOY["spec_n"]), TOY["seq_len"], TOY["overlap"], tok,
+                            MADGRAD)
+    # the noisy-prediction print of the reference also calls tokenizer.encode (lib.py:304); skip those entries
+    gold_lens = GOLD["ids_len_awmc"].tolist()
+    got = [len(e) for e in tok.encoded]
+    assert sum(got) <= sum(gold_lens)
+    np.testing.assert_allclose(np.exp(logits), np.exp(GOLD["logits_awmc"]), rtol=2e-4, atol=1e-7)
+    assert all(torch.equal(a, b) for a, b in zip(before, model.parameters()))

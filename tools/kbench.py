@@ -141,6 +141,38 @@ def main():
         n_out = 2048 + 256 * (nwin - 1)
         report("stitch(+cat)", [nwin, Tp, Cc], nwin * Tp * Cc * 4 + n_out * Cc * 4, med, best)
 
+    if want("softdtw"):
+        from dae.soft_dtw_cuda import softdtw_backward, softdtw_forward
+        for (B, N, M) in ((8, 4096, 4096), (8, 1024, 1024), (512, 256, 256)):
+            a = torch.rand(B, N, 2, generator=g, device="cuda")
+            b = torch.rand(B, M, 2, generator=g, device="cuda")
+            D = ((a[:, :, None, :] - b[:, None, :, :]) ** 2).sum(-1).contiguous()
+            med, best = tm.time(lambda: softdtw_forward(D, 1.0, 0.0), max(5, args.iters // 2))
+            report("softdtw_fwd", [B, N, M], 2 * B * N * M * 4, med, best)
+            _, R, Dc = softdtw_forward(D, 1.0, 0.0)
+            go = torch.ones(B, device="cuda")
+            med, best = tm.time(lambda: softdtw_backward(Dc, R, go, 1.0, 0.0), max(5, args.iters // 2))
+            report("softdtw_bwd", [B, N, M], 3 * B * N * M * 4, med, best)
+            del D, R, Dc
+
+    if want("beam"):
+        import numpy as np
+        from oracle.beam_oracle import peaky_log_probs
+        from dae.ctc_beam_search import _Search
+        from dae.ngram import NGramLM, read_arpa, write_synthetic_arpa
+        V = 31
+        write_synthetic_arpa("/tmp/kbench.arpa", V, order=4, counts=(None, 900, 200000, 800000), seed=4)
+        order, grams = read_arpa("/tmp/kbench.arpa")
+        lm = NGramLM(grams, order, V)
+        T = 180000
+        lp = torch.from_numpy(peaky_log_probs(T, V + 1, V, 3, sharp=5.0)).cuda()
+        for nseg in (360, 1):
+            offs = [int(x) for x in np.linspace(0, T, nseg + 1)]
+            sr = _Search(lp, offs, lm, 100, 0.45, 1.53, V, 0.0, 0.0, -6, 3.17, n_best=1)
+            med, best = tm.time(lambda: sr.run_all(), 3, warmup=1)
+            report("beam_search(beam=100,4-gram %d nodes %.0f MB)" % (lm.n_nodes, lm.nbytes() / 1e6), [T, V + 1, nseg],
+                   T * (V + 1) * 4, med, best, {"frames_per_s": T / med, "audio_hours_per_s_at_50fps": T / 50 / 3600 / med})
+
     print("launches:", C_.launch_count())
     if args.json:
         json.dump({"peak_gbs": peak, "peak_source": how, "rows": rows}, open(args.json, "w"), indent=1)

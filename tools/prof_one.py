@@ -51,6 +51,56 @@ def main():
             (loss / T).backward()
             torch.cuda.synchronize()
             print("lattice ms", s.elapsed_time(e), "loss", loss.item())
+    elif a.what == "greedy":
+        from dae.greedy import greedy_ids_device
+        lp = peaky(52000, 4096, 4095, g)
+        for _ in range(a.reps):
+            flush.add_(1.0)
+            greedy_ids_device(lp, 4095)
+        torch.cuda.synchronize()
+    elif a.what == "specaug":
+        from dae.augment import SpecAugment
+        spec = torch.randn(1, 80, 120000, device="cuda")
+        aug = SpecAugment(n_freq_masks=6, freq_mask_param=34)
+        for _ in range(a.reps):
+            flush.add_(1.0)
+            aug(spec[:, :, 2048:2048 + 16384], n_clean=1)
+        torch.cuda.synchronize()
+    elif a.what == "stitch":
+        from dae.stitch import stitch_flat, window_positions
+        nwin, Tp, C = 52, 2048, 4096
+        flat = torch.cat([peaky(Tp, C, C - 1, g) for _ in range(nwin)], 0)
+        starts = [2048 * i for i in range(nwin)]
+        pos = window_positions(starts, [16384] * nwin, [Tp] * nwin, 14336)
+        for _ in range(a.reps):
+            flush.add_(1.0)
+            stitch_flat(flat, [Tp * i for i in range(nwin)], pos, [Tp] * nwin)
+        torch.cuda.synchronize()
+    elif a.what == "softdtw":
+        from dae.soft_dtw_cuda import softdtw_backward, softdtw_forward
+        B, N, M = 8, 4096, 4096
+        x, y = torch.rand(B, N, 2, generator=g, device="cuda"), torch.rand(B, M, 2, generator=g, device="cuda")
+        D = ((x[:, :, None, :] - y[:, None, :, :]) ** 2).sum(-1).contiguous()
+        go = torch.ones(B, device="cuda")
+        for _ in range(a.reps):
+            flush.add_(1.0)
+            _, R, Dc = softdtw_forward(D, 1.0, 0.0)
+            softdtw_backward(Dc, R, go, 1.0, 0.0)
+        torch.cuda.synchronize()
+    elif a.what == "beam":
+        import numpy as np
+        from oracle.beam_oracle import peaky_log_probs
+        from dae.ctc_beam_search import _Search
+        from dae.ngram import NGramLM, read_arpa, write_synthetic_arpa
+        V, T, nseg = 31, 18000, 36
+        write_synthetic_arpa("/tmp/prof.arpa", V, order=4, counts=(None, 900, 20000, 80000), seed=4)
+        order, grams = read_arpa("/tmp/prof.arpa")
+        lm = NGramLM(grams, order, V)
+        lp = torch.from_numpy(peaky_log_probs(T, V + 1, V, 3, sharp=5.0)).cuda()
+        sr = _Search(lp, [int(v) for v in np.linspace(0, T, nseg + 1)], lm, 100, 0.45, 1.53, V, 0.0, 0.0, -6, 3.17, n_best=1)
+        for _ in range(a.reps):
+            sr.run_all()
+        torch.cuda.synchronize()
     else:
         raise SystemExit("unknown kernel family " + a.what)
 

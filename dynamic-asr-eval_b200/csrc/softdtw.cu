@@ -24,7 +24,8 @@ namespace dae {
 
 constexpr int kBand = 32;                 // rows per warp
 constexpr int kTile = 32;                 // columns per staged tile
-constexpr int kGrp = 8;                   // columns per export poll group
+constexpr int kGrp = 4;                   // columns per export poll group
+constexpr int kDepth = 1;                 // groups between requesting band-above values and using them
 constexpr float kLog2eF = 1.4426950408889634f;
 constexpr float kLn2F = 0.6931471805599453f;
 
@@ -55,47 +56,58 @@ __device__ __forceinline__ int2 ld_volatile_int2(const int2* p) {
   asm volatile("ld.volatile.global.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_volatile_int2(int2* p, int2 v) {
+  asm volatile("st.volatile.global.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ float ex2f_(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float lg2f_(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-// Stage one 32x32 tile (rows r0.., columns c0..) of a [N,M] matrix into smem[32][32]; out-of-range
-// elements are left untouched (never read by an active lane).  `flip` stages the flipped grid:
-// smem row i' holds matrix row N-1-(r0+i'), smem column x holds matrix column cbase+x where the
-// caller passes cbase = M - c0 - 32 (may be negative for the last, partial tile).
+constexpr int kRing = 4;                  // staged input tiles per matrix (power of two: ring index = col & 127)
+constexpr int kRingCols = kRing * kTile;  // 128
+constexpr int kOutCols = 2 * kTile;       // result ring: two tiles
+
+// Stage one 32-column tile (columns c0.. of the possibly flipped grid) of a [N,M] matrix into the smem
+// ring sm[32][128] at ring slot (c0/32)&3.  Out-of-range elements are left untouched (never read by an
+// active lane).  FLIP stages the flipped grid: smem row i' holds matrix row N-1-(r0+i'); the 32 columns
+// are stored in matrix order (cp.async cannot reverse inside a 16-byte chunk) and the reader indexes
+// them with (col ^ 31).
 template <bool FLIP>
 __device__ __forceinline__ void stage_tile(float* sm, const float* __restrict__ mat, int N, int M, int r0, int c0,
                                            int lane, bool vec) {
   const int cbase = FLIP ? (M - c0 - kTile) : c0;
+  float* dst0 = sm + ((c0 >> 5) & (kRing - 1)) * kTile;
   if (vec) {
-    // 8 lanes x 16 B cover one row; 4 rows per instruction
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < 8; ++it) {       // 8 lanes x 16 B cover one row; 4 rows per instruction
       const int ri = it * 4 + (lane >> 3);
       const int x = (lane & 7) * 4;
       const int row = FLIP ? (N - 1 - (r0 + ri)) : (r0 + ri);
       const int col = cbase + x;
-      if (row >= 0 && row < N && col >= 0 && col + 3 < M) {
-        cp_async16(sm + ri * kTile + x, mat + (int64_t)row * M + col);
-      } else if (row >= 0 && row < N) {
+      if (row >= 0 && row < N) {
+        if (col >= 0 && col + 3 < M) {
+          cp_async16(dst0 + ri * kRingCols + x, mat + (int64_t)row * M + col);
+        } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (col + e >= 0 && col + e < M) cp_async4s(sm + ri * kTile + x + e, mat + (int64_t)row * M + col + e);
+          for (int e = 0; e < 4; ++e)
+            if (col + e >= 0 && col + e < M) cp_async4s(dst0 + ri * kRingCols + x + e, mat + (int64_t)row * M + col + e);
+        }
       }
     }
   } else {
     for (int ri = 0; ri < kBand; ++ri) {
       const int row = FLIP ? (N - 1 - (r0 + ri)) : (r0 + ri);
       const int col = cbase + lane;
-      if (row >= 0 && row < N && col >= 0 && col < M) cp_async4s(sm + ri * kTile + lane, mat + (int64_t)row * M + col);
+      if (row >= 0 && row < N && col >= 0 && col < M) cp_async4s(dst0 + ri * kRingCols + lane, mat + (int64_t)row * M + col);
     }
   }
 }
 
-// Flush a finished 32x32 result tile to the [N,M] output with coalesced stores.
+// Flush a finished 32-column result tile (ring sm[32][64], slot (c0/32)&1) with coalesced stores.
 template <bool FLIP>
 __device__ __forceinline__ void flush_tile(const float* sm, float* __restrict__ mat, int N, int M, int r0, int c0,
                                            int lane, bool vec) {
   const int cbase = FLIP ? (M - c0 - kTile) : c0;
+  const float* src0 = sm + ((c0 >> 5) & 1) * kTile;
   if (vec) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -105,11 +117,11 @@ __device__ __forceinline__ void flush_tile(const float* sm, float* __restrict__ 
       const int col = cbase + x;
       if (row >= 0 && row < N) {
         if (col >= 0 && col + 3 < M) {
-          st_stream4(mat + (int64_t)row * M + col, *reinterpret_cast<const float4*>(sm + ri * kTile + x));
+          st_stream4(mat + (int64_t)row * M + col, *reinterpret_cast<const float4*>(src0 + ri * kOutCols + x));
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            if (col + e >= 0 && col + e < M) mat[(int64_t)row * M + col + e] = sm[ri * kTile + x + e];
+            if (col + e >= 0 && col + e < M) mat[(int64_t)row * M + col + e] = src0[ri * kOutCols + x + e];
         }
       }
     }
@@ -117,171 +129,178 @@ __device__ __forceinline__ void flush_tile(const float* sm, float* __restrict__ 
     for (int ri = 0; ri < kBand; ++ri) {
       const int row = FLIP ? (N - 1 - (r0 + ri)) : (r0 + ri);
       const int col = cbase + lane;
-      if (row >= 0 && row < N && col >= 0 && col < M) mat[(int64_t)row * M + col] = sm[ri * kTile + lane];
+      if (row >= 0 && row < N && col >= 0 && col < M) mat[(int64_t)row * M + col] = src0[ri * kOutCols + lane];
     }
   }
 }
 
-template <bool BWD>
+template <bool BWD, bool PRUNE>
 __global__ void __launch_bounds__(256)
 softdtw_wave_kernel(SdtwParams P, int vec, int smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int RING = BWD ? 3 : 4;       // staged input tiles per matrix
-  constexpr int AHEAD = RING - 2;         // tiles prefetched beyond the two in use
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* sm = reinterpret_cast<float*>(smem_raw + (size_t)warp * smem_per_warp);
-  float* sD = sm;                                           // [RING][32][32]
-  float* sR = BWD ? (sD + RING * kBand * kTile) : nullptr;  // [RING][32][32] (backward only)
-  float* sO = (BWD ? sR : sD) + RING * kBand * kTile;       // [2][32][32]
+  float* sD = sm;                                            // [32][128]
+  float* sR = BWD ? (sD + kBand * kRingCols) : nullptr;      // [32][128] (backward only)
+  float* sO = (BWD ? sR : sD) + kBand * kRingCols;           // [32][64]
+  const float* sDl = sD + lane * kRingCols;
+  const float* sRl = BWD ? (sR + lane * kRingCols) : nullptr;
+  float* sOl = sO + lane * kOutCols;
   const int N = P.N, M = P.M;
   const int n_agents = P.B * P.nbands;
   const int n_tiles = (M + kTile - 1) / kTile;
-  const float ig2 = kLog2eF / P.gamma;                      // 1/gamma in log2 units
+  const float ig2 = kLog2eF / P.gamma;                       // 1/gamma in log2 units
   const float g_ln2 = P.gamma * kLn2F;
-  const bool prune = P.bandwidth > 0.0f;
   const float INF = CUDART_INF_F;
+  const int steps = M + kBand - 1;
+  const int k_last = (steps - 1) >> 5;
+  const int flipx = BWD ? (kTile - 1) : 0;                   // flipped tiles are stored in matrix order
 
   for (;;) {
     int tk = 0;
     if (lane == 0) tk = atomicAdd(P.ticket, 1);
     tk = __shfl_sync(0xffffffffu, tk, 0);
     if (tk >= n_agents) break;
-    const int band = tk / P.B, b = tk - band * P.B;         // (band, sample) order
-    const int r0 = band * kBand;                            // first (flipped) row of this band
-    const int frow = r0 + lane;                             // this lane's (flipped) row
+    const int band = tk / P.B, b = tk - band * P.B;          // (band, sample) order
+    const int r0 = band * kBand;                             // first (flipped) row of this band
+    const int frow = r0 + lane;
     const bool row_ok = frow < N;
-    const int row = BWD ? (N - 1 - frow) : frow;            // matrix row
+    const int row = BWD ? (N - 1 - frow) : frow;             // matrix row
     const float* Db = P.D + (int64_t)b * N * M;
     float* Rb = P.R + (int64_t)b * N * M;
     float* Ob = BWD ? (P.E + (int64_t)b * N * M) : Rb;
     int2* exp_mine = P.exp_buf + ((int64_t)b * P.nbands + band) * P.Mp;
     const int2* exp_up = band > 0 ? (P.exp_buf + ((int64_t)b * P.nbands + band - 1) * P.Mp) : nullptr;
-    const float seed = BWD ? P.gout[b * P.gout_stride] : 0.0f;
+    const bool publish = (lane == kBand - 1) && (band + 1 < P.nbands);
+    // W of the upper band's bottom row (backward): R - D read straight from global, column index flipped
+    const float* upR = BWD && band > 0 ? (Rb + (int64_t)(N - r0) * M) : nullptr;
+    const float* upD = BWD && band > 0 ? (Db + (int64_t)(N - r0) * M) : nullptr;
 
-    // prologue: stage tiles 0 .. AHEAD-1 (tile k+AHEAD is staged when lane 0 enters tile k)
-    for (int k = 0; k < AHEAD && k < n_tiles; ++k) {
-      stage_tile<BWD>(sD + (k % RING) * kBand * kTile, Db, N, M, r0, k * kTile, lane, vec);
-      if (BWD) stage_tile<BWD>(sR + (k % RING) * kBand * kTile, Rb, N, M, r0, k * kTile, lane, vec);
+    __syncwarp();
+    // prologue: tiles 0 and 1 (tile k+2 is staged when lane 0 enters tile k)
+    int staged = 0;
+    for (; staged < 2 && staged < n_tiles; ++staged) {
+      stage_tile<BWD>(sD, Db, N, M, r0, staged * kTile, lane, vec);
+      if (BWD) stage_tile<BWD>(sR, Rb, N, M, r0, staged * kTile, lane, vec);
       cp_commit();
     }
-    int staged = (AHEAD < n_tiles) ? AHEAD : n_tiles;             // tiles staged so far
 
-    // per-lane wavefront state
-    float left_v = BWD ? 0.0f : INF, left_w = -INF;         // own previous cell (value, W)
-    float up_v = BWD ? 0.0f : INF, up_w = -INF;             // upper lane's previous-step cell
-    float my_v = BWD ? 0.0f : INF, my_w = -INF;             // this lane's latest cell
-    // bottom row of the band above, one poll group (kGrp columns) at a time, lanes 0..kGrp-1 hold it
-    float ab_v = BWD ? 0.0f : INF, ab_w = -INF;             // current group
-    const float r_corner = BWD ? Rb[(int64_t)(N - 1) * M + (M - 1)] : 0.0f;
-
-    const int steps = M + kBand - 1;
-    for (int p = 0; p < steps; ++p) {
-      if ((p & (kTile - 1)) == 0) {
-        const int k = p >> 5;                               // lane 0 enters tile k
-        // slot (k+AHEAD)%RING was last used by tile k-2, which no lane touches any more
-        if (staged < n_tiles && staged <= k + AHEAD) {
-          stage_tile<BWD>(sD + (staged % RING) * kBand * kTile, Db, N, M, r0, staged * kTile, lane, vec);
-          if (BWD) stage_tile<BWD>(sR + (staged % RING) * kBand * kTile, Rb, N, M, r0, staged * kTile, lane, vec);
-          cp_commit();
-          ++staged;
-        }
-        if (k < n_tiles) {
-          // tile k must have landed; the tiles staged after it may stay in flight
-          const int newer = staged - 1 - k;
-          if (newer >= 2) cp_wait<2>(); else if (newer == 1) cp_wait<1>(); else cp_wait<0>();
-          __syncwarp();
-        }
-        if (k >= 2 && k - 2 < n_tiles) {                    // tile k-2 is complete: flush it
-          flush_tile<BWD>(sO + ((k - 2) & 1) * kBand * kTile, Ob, N, M, r0, (k - 2) * kTile, lane, vec);
-          __syncwarp();
-        }
+    // Wavefront state.  Borders come from the initial values: before a lane's first cell its `left` is
+    // the left border and the upper lane still holds its own initial (border) value.
+    float my_v = BWD ? 0.0f : INF, my_w = -INF;              // this lane's latest cell
+    float up_v = my_v, up_w = -INF;                          // upper lane's cell one step ago (= diagonal)
+    if (band == 0 && lane == 0) {                            // the corner the recursion starts from
+      up_v = BWD ? P.gout[b * P.gout_stride] : 0.0f;
+      up_w = BWD ? Rb[(int64_t)(N - 1) * M + (M - 1)] : 0.0f;
+    }
+    float ab_v = BWD ? 0.0f : INF, ab_w = -INF;              // bottom row of the band above, kGrp columns
+    // export words of the band above are requested kDepth groups before they are needed (tag-in-data:
+    // {value, column+1}); lanes 0..kGrp-1 hold one column each
+    int2 nx[kDepth];
+    float nx_r[kDepth], nx_d[kDepth];
+#pragma unroll
+    for (int u = 0; u < kDepth; ++u) {
+      nx[u] = make_int2(0, 0); nx_r[u] = 0.0f; nx_d[u] = 0.0f;
+      const int col = u * kGrp + lane;
+      if (exp_up && lane < kGrp && col < M) {
+        nx[u] = ld_volatile_int2(exp_up + col);
+        if (BWD) { nx_r[u] = __ldcg(upR + (M - 1 - col)); nx_d[u] = __ldcg(upD + (M - 1 - col)); }
       }
-      if ((p & (kGrp - 1)) == 0 && p < M) {                 // lane 0 enters export group p/kGrp
-        if (exp_up) {
-          const int col = p + lane;                         // lanes 0..kGrp-1 poll their column
+    }
+
+    int p = 0;
+    int j = -lane;                                           // this lane's (flipped) column at step p
+    for (int k = 0; k <= k_last; ++k) {
+      // ---- once per 32 steps: lane 0 enters tile k
+      if (staged < n_tiles && staged <= k + 2) {             // ring slot (k+2)&3 was tile k-2's: free
+        stage_tile<BWD>(sD, Db, N, M, r0, staged * kTile, lane, vec);
+        if (BWD) stage_tile<BWD>(sR, Rb, N, M, r0, staged * kTile, lane, vec);
+        cp_commit();
+        ++staged;
+      }
+      if (k < n_tiles) {
+        const int newer = staged - 1 - k;                    // tiles staged after tile k may stay in flight
+        if (newer >= 2) cp_wait<2>(); else if (newer == 1) cp_wait<1>(); else cp_wait<0>();
+        __syncwarp();
+      }
+      if (k >= 2 && k - 2 < n_tiles) {                       // tile k-2 is complete: flush it
+        __syncwarp();
+        flush_tile<BWD>(sO, Ob, N, M, r0, (k - 2) * kTile, lane, vec);
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int gq = 0; gq < kTile / kGrp; ++gq) {
+        // ---- once per kGrp steps: take the kGrp band-above values requested kDepth groups ago (re-poll only
+        // if they had not been published yet), then request the group needed kDepth groups from now.
+        if (exp_up && p < M) {
+          constexpr int us = 0;                              // kDepth == 1: a single request in flight
+          const int col = p + lane;
           const bool need = lane < kGrp && col < M;
-          int2 w = make_int2(0, 0);
+          int2 w = nx[us];
           for (;;) {
-            if (need) w = ld_volatile_int2(exp_up + col);
             if (__all_sync(0xffffffffu, !need || w.y == col + 1)) break;
+            if (need) w = ld_volatile_int2(exp_up + col);
           }
           ab_v = __int_as_float(w.x);
-          if (BWD && need) {                                // W of the upper band's bottom row = R - D there
-            const int urow = N - 1 - (r0 - 1), ucol = M - 1 - col;
-            const float ur = __ldcg(Rb + (int64_t)urow * M + ucol);
-            ab_w = isinf(ur) ? -INF : ur - __ldcg(Db + (int64_t)urow * M + ucol);
+          if (BWD) ab_w = (PRUNE && isinf(nx_r[us])) ? -INF : nx_r[us] - nx_d[us];
+          const int col2 = col + kDepth * kGrp;
+          if (lane < kGrp && col2 < M) {
+            nx[us] = ld_volatile_int2(exp_up + col2);
+            if (BWD) { nx_r[us] = __ldcg(upR + (M - 1 - col2)); nx_d[us] = __ldcg(upD + (M - 1 - col2)); }
           }
-        } else {
-          ab_v = BWD ? 0.0f : INF;
-          ab_w = -INF;
         }
-      }
-      const int j = p - lane;                               // this lane's (flipped) column
-      // upper neighbour of this step = upper lane's latest cell (its column is j as well)
-      float nu_v = __shfl_up_sync(0xffffffffu, my_v, 1);
-      float nu_w = BWD ? __shfl_up_sync(0xffffffffu, my_w, 1) : 0.0f;
-      {
-        const float a_v = __shfl_sync(0xffffffffu, ab_v, p & (kGrp - 1));
-        const float a_w = BWD ? __shfl_sync(0xffffffffu, ab_w, p & (kGrp - 1)) : 0.0f;
-        if (lane == 0) { nu_v = a_v; nu_w = a_w; }
-      }
-      float dg_v = up_v, dg_w = up_w;                       // diagonal = upper neighbour one step ago
-      float lf_v = left_v, lf_w = left_w;
-      if (j == 0) {                                         // left border of the grid
-        lf_v = BWD ? 0.0f : INF; lf_w = -INF;
-        dg_v = BWD ? 0.0f : INF; dg_w = -INF;
-        if (frow == 0) { dg_v = BWD ? seed : 0.0f; dg_w = r_corner; }
-      }
-      const bool active = row_ok && j >= 0 && j < M;
-      const int jj = active ? j : 0;
-      const int tslot = (jj >> 5) % RING, tcol = jj & 31;
-      const int sidx = BWD ? (kTile - 1 - tcol) : tcol;     // flipped tiles are stored unflipped along x
-      const float d = sD[tslot * kBand * kTile + lane * kTile + sidx];
-      float res_v, res_w = 0.0f;
-      // 1-based indices differ by the same amount in both orientations
-      const int ci = BWD ? (M - 1 - jj) : jj;
-      const bool pruned = prune && fabsf((float)(row - ci)) > P.bandwidth;
-      if (!BWD) {
-        // R = D + softmin_gamma(diag, up, left)  (soft_dtw_cuda.py:65-72)
-        const float mn = fminf(fminf(dg_v, nu_v), lf_v);
-        float sm_;
-        if (mn == INF) {
-          sm_ = INF;
-        } else {
-          const float s = ex2f_((mn - dg_v) * ig2) + ex2f_((mn - nu_v) * ig2) + ex2f_((mn - lf_v) * ig2);
-          sm_ = mn - g_ln2 * lg2f_(s);
+#pragma unroll
+        for (int q = 0; q < kGrp; ++q, ++p, ++j) {
+          // upper neighbour: the upper lane's latest cell (its column equals ours); lane 0 takes the band above
+          float nu_v = __shfl_up_sync(0xffffffffu, my_v, 1);
+          float nu_w = BWD ? __shfl_up_sync(0xffffffffu, my_w, 1) : 0.0f;
+          {
+            const float a_v = __shfl_sync(0xffffffffu, ab_v, q);
+            const float a_w = BWD ? __shfl_sync(0xffffffffu, ab_w, q) : 0.0f;
+            if (lane == 0) { nu_v = a_v; nu_w = a_w; }
+          }
+          const int sc = (j & (kRingCols - 1)) ^ flipx;
+          const float d = sDl[sc];
+          const bool active = row_ok && (unsigned)j < (unsigned)M;
+          float res_v, res_w = 0.0f;
+          if (!BWD) {
+            // R = D + softmin_gamma(diag, up, left)  (soft_dtw_cuda.py:65-72); left = my_v, diag = up_v.
+            // Without pruning every cell has a finite predecessor, so mn is finite and (mn - inf) is safe.
+            const float mn = fminf(fminf(up_v, nu_v), my_v);
+            const float s = ex2f_((mn - up_v) * ig2) + ex2f_((mn - nu_v) * ig2) + ex2f_((mn - my_v) * ig2);
+            res_v = d + (mn - g_ln2 * lg2f_(s));
+            if (PRUNE) {
+              if (mn == INF || fabsf((float)(row - j)) > P.bandwidth) res_v = INF;
+            }
+          } else {
+            // E = E_dn*a + E_right*b + E_diag*c, a,b,c = exp((W[.] - R[i,j]) / gamma)  (:100-108)
+            float r = sRl[sc];
+            if (PRUNE && isinf(r)) r = -INF;                 // :96-97 (only pruned cells hold +inf)
+            res_w = r - d;
+            const float a = ex2f_((nu_w - r) * ig2), bb = ex2f_((my_w - r) * ig2), c = ex2f_((up_w - r) * ig2);
+            res_v = nu_v * a + my_v * bb + up_v * c;
+            if (PRUNE) {
+              if (r == -INF) { res_v = 0.0f; res_w = -INF; }
+              if (fabsf((float)(row - (M - 1 - j))) > P.bandwidth) res_v = 0.0f;
+            }
+          }
+          up_v = nu_v; up_w = nu_w;
+          if (active) {
+            my_v = res_v; my_w = res_w;
+            sOl[(j & (kOutCols - 1)) ^ flipx] = res_v;
+            // publish the band's bottom row for the band below: {value, column+1} in one 8-byte store
+            if (publish) st_volatile_int2(exp_mine + j, make_int2(__float_as_int(res_v), j + 1));
+          }
         }
-        res_v = pruned ? INF : d + sm_;
-      } else {
-        // E = E_dn*a + E_right*b + E_diag*c with a,b,c = exp((W[.] - R[i,j]) / gamma)  (:100-108)
-        float r = sR[tslot * kBand * kTile + lane * kTile + sidx];
-        if (isinf(r)) r = -INF;                             // :96-97
-        res_w = r - d;
-        const float a = ex2f_((nu_w - r) * ig2), bb = ex2f_((lf_w - r) * ig2), c = ex2f_((dg_w - r) * ig2);
-        res_v = pruned ? 0.0f : (nu_v * a + lf_v * bb + dg_v * c);
-        if (pruned || r == -INF) { res_v = 0.0f; }
-        if (r == -INF) res_w = -INF;
-      }
-      up_v = nu_v; up_w = nu_w;
-      if (active) {
-        my_v = res_v; my_w = res_w;
-        left_v = res_v; left_w = res_w;
-        sO[((jj >> 5) & 1) * kBand * kTile + lane * kTile + sidx] = res_v;
-        // publish the band's bottom row for the band below: {value, column+1} in one 8-byte store
-        if (lane == kBand - 1) exp_mine[j] = make_int2(__float_as_int(res_v), j + 1);
       }
     }
-    // flush the last (up to two) tiles
+    // flush the tiles not yet flushed inside the loop (at most two)
     __syncwarp();
-    for (int k = (n_tiles >= 2 ? n_tiles - 2 : 0); k < n_tiles; ++k) {
-      // tiles already flushed inside the loop: k <= (steps-1)/32 - 2
-      if (k <= ((steps - 1) >> 5) - 2) continue;
-      flush_tile<BWD>(sO + (k & 1) * kBand * kTile, Ob, N, M, r0, k * kTile, lane, vec);
-    }
+    for (int k = (k_last - 1 > 0 ? k_last - 1 : 0); k < n_tiles; ++k)
+      flush_tile<BWD>(sO, Ob, N, M, r0, k * kTile, lane, vec);
     __syncwarp();
     if (!BWD && band == P.nbands - 1) {
-      // R[N-1, M-1] lives in lane (N-1) - r0 of the last band
-      const float v = __shfl_sync(0xffffffffu, my_v, (N - 1) - r0);
+      const float v = __shfl_sync(0xffffffffu, my_v, (N - 1) - r0);   // R[N-1, M-1]
       if (lane == 0) P.out[b] = v;
     }
   }
@@ -314,16 +333,17 @@ static int softdtw_launch(const float* D, float* R, float* E, float* out, const 
   P.exp_buf = reinterpret_cast<int2*>(reinterpret_cast<char*>(scratch) + 256);
   P.gamma = gamma; P.bandwidth = bandwidth;
   DAE_CUDA(cudaMemsetAsync(scratch, 0, dae_softdtw_scratch_bytes(B, N, M), st));
-  constexpr int RING = BWD ? 3 : 4;
-  const int smem_per_warp = (RING * (BWD ? 2 : 1) + 2) * kBand * kTile * 4;
-  const int warps = BWD ? 6 : 8;
+  const int smem_per_warp = ((BWD ? 2 : 1) * kBand * kRingCols + kBand * kOutCols) * 4;   // 24 KB / 40 KB
+  const int warps = BWD ? 5 : 8;
   const int smem = smem_per_warp * warps;
-  DAE_CUDA(cudaFuncSetAttribute(softdtw_wave_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const bool prune = bandwidth > 0.0f;
+  auto kern = prune ? softdtw_wave_kernel<BWD, true> : softdtw_wave_kernel<BWD, false>;
+  DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int agents = B * P.nbands;
   int grid = (agents + warps - 1) / warps;
   if (grid > kNumSMs) grid = kNumSMs;                     // persistent: one CTA per SM, tickets do the rest
   const int vec = aligned16(D) && aligned16(R) && (!BWD || aligned16(E)) && (M % 4 == 0);
-  softdtw_wave_kernel<BWD><<<grid, warps * 32, smem, st>>>(P, vec, smem_per_warp);
+  kern<<<grid, warps * 32, smem, st>>>(P, vec, smem_per_warp);
   DAE_LAUNCH_OK();
   return 0;
 }

@@ -78,7 +78,7 @@ def main():
         torch.cuda.synchronize()
     elif a.what == "softdtw":
         from dae.soft_dtw_cuda import softdtw_backward, softdtw_forward
-        B, N, M = 8, 4096, 4096
+        B, N, M = 8, a.n if a.n > 1 else 4096, a.n if a.n > 1 else 4096
         x, y = torch.rand(B, N, 2, generator=g, device="cuda"), torch.rand(B, M, 2, generator=g, device="cuda")
         D = ((x[:, :, None, :] - y[:, None, :, :]) ** 2).sum(-1).contiguous()
         go = torch.ones(B, device="cuda")

@@ -37,8 +37,22 @@ struct CtcScratch {           // carved out of the caller's scratch buffer
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Thread geometry of the lattice kernel: P state pairs per consumer thread, NTc consumer threads.
+// Every consumer thread owns real or dummy pairs, so lattice rows are 2*NTc*P floats wide.
+static inline void lat_geometry(int Lmax, int& P, int& NTc) {
+  constexpr int kMaxConsumers = kLatThreads - 64;        // two helper warps: centring + TMA
+  const int pairs = Lmax + 1;
+  P = (pairs + kMaxConsumers - 1) / kMaxConsumers;
+  P = P <= 1 ? 1 : (P <= 2 ? 2 : 4);
+  static const int forced = [] { const char* e = getenv("DAE_CTC_PAIRS"); return e ? atoi(e) : 0; }();
+  if ((forced == 1 || forced == 2 || forced == 4) && (pairs + forced - 1) / forced <= kMaxConsumers) P = forced;
+  NTc = (((pairs + P - 1) / P + 31) / 32) * 32;
+}
+
 static inline size_t ctc_carve(CtcScratch& s, void* base, int T, int N, int Lmax) {
-  s.Sp = (int)align_up((size_t)2 * Lmax + 1, 4);
+  int P_, NTc_;
+  lat_geometry(Lmax, P_, NTc_);
+  s.Sp = 2 * NTc_ * P_;
   s.Lp = (int)align_up((size_t)(Lmax > 0 ? Lmax : 1), 4);
   char* p = (char*)base;
   size_t off = 0;
@@ -117,6 +131,18 @@ __device__ __forceinline__ float lse2_2(float a, float b) {
   if (m == -CUDART_INF_F) return m;
   return m + fast_lg2(1.0f + fast_ex2(lo - m));
 }
+// Branch-free variants for the lattice: dead states hold the finite sentinel kDead instead of -inf
+// (kDead + anything finite == kDead in fp32, and kDead - kDead == 0, so no NaN can appear).
+constexpr float kDead = -1.0e30f;
+__device__ __forceinline__ float lse2_n(float a, float b) {
+  const float m = fmaxf(a, b), lo = fminf(a, b);
+  return m + fast_lg2(1.0f + fast_ex2(lo - m));
+}
+__device__ __forceinline__ float lse3_n(float a, float b, float c) {
+  const float lo = fminf(a, b), hi = fmaxf(a, b);
+  const float m = fmaxf(hi, c), mid = fminf(hi, c);
+  return m + fast_lg2(1.0f + fast_ex2(mid - m) + fast_ex2(lo - m));
+}
 
 struct LatSmem {              // byte offsets into dynamic shared memory (host and device agree)
   int bars, cx, wmx, lab, a0, a1, rows, row_stride, stages, total;
@@ -137,29 +163,26 @@ __host__ __device__ inline LatSmem lat_smem_layout(int C, int Lp, int Sp, int ma
   return m;
 }
 
-// One lattice step for the P state pairs of a consumer thread.  `prev`/`cur` are the ping-pong
-// lattice rows, `xrow` the emission row of this frame in the smem ring, cx = (c, xb).
+// One lattice step for the P state pairs of a consumer thread, branch-free.  `prev`/`cur` are the
+// ping-pong lattice rows (this thread's pair j lives at index p2[j] = 2*pair), `xrow` the emission row
+// of this frame in the smem ring, cx = (c, xb).  lneg[j] is kDead for pairs whose label state does
+// not exist (pair >= L), which also keeps every dummy pair past the end of the lattice dead.
 template <int P>
 __device__ __forceinline__ void lattice_step(const float* __restrict__ prev, float* __restrict__ cur,
                                              const float* __restrict__ xrow, float2 cx, float* __restrict__ orow,
-                                             const int (&xoff)[P], const bool (&skip)[P], const int (&pidx)[P],
-                                             int L, int* __restrict__ wmx_slot, int warp, int lane) {
-  float vmax = -CUDART_INF_F;
+                                             const int (&xoff)[P], const bool (&skip)[P], const int (&p2)[P],
+                                             const float (&lneg)[P], int* __restrict__ wmx_slot, int warp, int lane) {
+  float vmax = kDead;
 #pragma unroll
   for (int j = 0; j < P; ++j) {
-    const int p = pidx[j];
-    if (p <= L) {
-      const float pm1 = prev[2 * p - 1];
-      const float2 pp = *reinterpret_cast<const float2*>(prev + 2 * p);     // (blank, label) of this pair
-      const float xl = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(xrow) + xoff[j]);
-      const float vb = cx.y + lse2_2(pp.x, pm1);
-      float vl = -CUDART_INF_F;
-      if (p < L) vl = fmaf(xl, kLog2e, -cx.x) + lse3_2(pp.y, pp.x, skip[j] ? pm1 : -CUDART_INF_F);
-      *reinterpret_cast<float2*>(cur + 2 * p) = make_float2(vb, vl);
-      if (p < L) *reinterpret_cast<float2*>(orow + 2 * p) = make_float2(vb, vl);
-      else orow[2 * p] = vb;
-      vmax = fmaxf(vmax, fmaxf(vb, vl));
-    }
+    const float pm1 = prev[p2[j] - 1];
+    const float2 pp = *reinterpret_cast<const float2*>(prev + p2[j]);       // (blank, label) of this pair
+    const float xl = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(xrow) + xoff[j]);
+    const float vb = cx.y + lse2_n(pp.x, pm1);
+    const float vl = (fmaf(xl, kLog2e, -cx.x) + lneg[j]) + lse3_n(pp.y, pp.x, skip[j] ? pm1 : kDead);
+    *reinterpret_cast<float2*>(cur + p2[j]) = make_float2(vb, vl);
+    *reinterpret_cast<float2*>(orow + p2[j]) = make_float2(vb, vl);
+    vmax = fmaxf(vmax, fmaxf(vb, vl));
   }
   const int wmax = __reduce_max_sync(0xffffffffu, f2ord(vmax));
   if (lane == 0) wmx_slot[warp] = wmax;
@@ -182,7 +205,7 @@ ctc_lattice_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, 
   const int n = blockIdx.y;
   const int N = gridDim.y;
   const int dir = blockIdx.x;             // 0 alpha, 1 beta
-  const int NTc = blockDim.x - 32;        // consumer threads
+  const int NTc = blockDim.x - 64;        // consumer threads (the last two warps are helpers)
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const bool producer = tid >= NTc;
@@ -217,12 +240,12 @@ ctc_lattice_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, 
     lab[k] = (int)tgt[n * tgt_stride + src];
   }
   if (tid < 4) {
-    a0[tid - 4] = -CUDART_INF_F;
-    a1[tid - 4] = -CUDART_INF_F;
+    a0[tid - 4] = kDead;
+    a1[tid - 4] = kDead;
   }
-  for (int i = tid; i < 128; i += blockDim.x) wmx[i] = f2ord(-CUDART_INF_F);
+  for (int i = tid; i < 128; i += blockDim.x) wmx[i] = f2ord(kDead);
   if (tid == 0) {
-    for (int r = 0; r < R; ++r) mbar_init(&full[r], vec ? 1u : 32u);
+    for (int r = 0; r < R; ++r) mbar_init(&full[r], vec ? 1u : 32u);   // arrivals come from the tma warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -234,8 +257,12 @@ ctc_lattice_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, 
   const int64_t t_first = dir ? (Tn - 1) : 0;
 
   if (producer) {
-    // ------------------------------------------------------------------ producer warp
-    double* offs = (dir ? sc.off_b : sc.off_a) + (int64_t)n * T;
+    // ------------------------------------------------------------------ two helper warps
+    // warp `NTc/32`   (ctr): waits for the next emission row, turns the per-warp maxima of step t-1 into the
+    //                        centring constant of step t+1, accumulates offsets, publishes (c, blank emission).
+    // warp `NTc/32+1` (tma): keeps the emission ring full: after every frame barrier it re-arms the slot
+    //                        that was just consumed with one TMA bulk copy.
+    const bool is_tma = (tid - NTc) >= 32;
     const uint32_t row_bytes = (uint32_t)C * 4u;
     auto fill = [&](int slot, const float* src) {
       float* dst = reinterpret_cast<float*>(rows + (size_t)slot * lay.row_stride);
@@ -249,11 +276,24 @@ ctc_lattice_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, 
         cp_async_arrive(&full[slot]);
       }
     };
-    const float* src_next = base + t_first * sT;      // row of the next lattice step to enqueue
-    int t_fill = 0;
-    for (; t_fill < R && t_fill < Tn; ++t_fill, src_next += xstep) fill(t_fill, src_next);
-    int fill_slot = 0;                                 // slot that frees up after the current step
-
+    if (is_tma) {
+      const float* src_next = base + t_first * sT;    // row of the next lattice step to enqueue
+      int t_fill = 0;
+      for (; t_fill < R && t_fill < Tn; ++t_fill, src_next += xstep) fill(t_fill, src_next);
+      int fill_slot = 0;                               // slot that frees up after the current step
+      __syncthreads();                                 // "start"
+      for (int t = 0; t < Tn; ++t) {
+        __syncthreads();                               // end of step t
+        if (t_fill < Tn) {                             // the slot consumed at step t is free for step t+R
+          fill(fill_slot, src_next);
+          src_next += xstep;
+          ++t_fill;
+        }
+        if (++fill_slot == R) fill_slot = 0;
+      }
+      return;
+    }
+    double* offs = (dir ? sc.off_b : sc.off_a) + (int64_t)n * T;
     // step 0 constants
     mbar_wait(&full[0], 0);
     if (lane == 0) {
@@ -263,52 +303,46 @@ ctc_lattice_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, 
     __syncthreads();                                   // "start": consumers may run step 0
 
     double off_acc = 0.0;                              // A_t: total offset removed up to step t
-    double a_prev = 0.0;                               // A_{t-1}
-    double m_prev2 = 0.0;                              // true maximum M_{t-2} = max~_{t-2} + A_{t-2}
-    bool have_prev2 = false;
+    float c_t = 0.0f, c_tm1 = 0.0f;                    // centring constants of steps t and t-1
+    float m_tm2 = 0.0f;                                // centred maximum of step t-2
+    bool have_tm2 = false;
     int wslot = 1 % R;                                 // ring slot of step t+1
     uint32_t wphase = (1 / R) & 1;
     int64_t tt_next = t_first + (dir ? -1 : 1);        // actual frame index of step t+1
     for (int t = 0; t < Tn; ++t) {
       if (t + 1 < Tn) {
         mbar_wait(&full[wslot], wphase);
+        const float xbl = reinterpret_cast<const float*>(rows + (size_t)wslot * lay.row_stride)[blank];
         // Centring constant of step t+1.  The newest maxima available are those of step t-1 (lag 2), so
-        // extrapolate the per-step drift: aim A_{t+1} at M_{t-1} + 2*(M_{t-1} - M_{t-2}).  Any value is
-        // valid (it is only a shift); a good one keeps the stored lattice near 0 where fp32 is densest.
+        // extrapolate the drift: aim A_{t+1} at M_{t-1} + 2*(M_{t-1} - M_{t-2}), all in small fp32 terms
+        // relative to the running offset.  Any value is valid (it is only a shift); a good one keeps the
+        // stored lattice near 0 where fp32 is densest.
         float c = 0.0f;
         if (t >= 1) {
-          int v = (lane < n_cwarps) ? wmx[((t - 1) & 3) * 32 + lane] : f2ord(-CUDART_INF_F);
+          int v = (lane < n_cwarps) ? wmx[((t - 1) & 3) * 32 + lane] : f2ord(kDead);
           v = __reduce_max_sync(0xffffffffu, v);
-          const float mt = ord2f(v);
-          if (mt != -CUDART_INF_F) {
-            const double m1 = (double)mt + a_prev;
-            const double drift = have_prev2 ? (m1 - m_prev2) : 0.0;
-            c = (float)(m1 + 2.0 * drift - off_acc);
-            m_prev2 = m1;
-            have_prev2 = true;
+          const float mt = ord2f(v);                   // centred maximum of step t-1
+          if (mt > -1.0e29f) {                         // otherwise the whole lattice is dead (infeasible)
+            const float drift = have_tm2 ? (mt - m_tm2 + c_tm1) : 0.0f;
+            c = (mt - c_t) + 2.0f * drift;
+            m_tm2 = mt;
+            have_tm2 = true;
           } else {
-            have_prev2 = false;
+            have_tm2 = false;
           }
         }
-        a_prev = off_acc;
-        off_acc += (double)c;                            // warp-uniform
+        c_tm1 = c_t;
+        c_t = c;
+        off_acc += (double)c;                          // warp-uniform
         if (lane == 0) {
-          offs[tt_next] = off_acc;
-          const float xbl = reinterpret_cast<const float*>(rows + (size_t)wslot * lay.row_stride)[blank];
           cxs[(t + 1) & 3] = make_float2(c, fmaf(xbl, kLog2e, -c));
+          offs[tt_next] = off_acc;
         }
         if (++wslot == R) { wslot = 0; wphase ^= 1u; }
         tt_next += dir ? -1 : 1;
       }
       __syncthreads();                                 // end of step t
-      if (t_fill < Tn) {                               // the slot consumed at step t is free for step t+R
-        fill(fill_slot, src_next);
-        src_next += xstep;
-        ++t_fill;
-      }
-      if (++fill_slot == R) fill_slot = 0;
     }
-    if (lane == 0) sc.ll2[2 * N + dir * N + n] = off_acc;   // total removed offset (consumer 0 adds the tail)
     return;
   }
 
@@ -327,17 +361,20 @@ ctc_lattice_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, 
       sc.leader[(int64_t)n * sc.Lp + k] = first;
     }
   }
-  int xoff[P], pidx[P];
+  int xoff[P], p2[P];
   bool skip[P];
+  float lneg[P];
 #pragma unroll
   for (int j = 0; j < P; ++j) {
     const int p = tid + j * NTc;
-    pidx[j] = p;
+    p2[j] = 2 * p;
     xoff[j] = blank * 4;
     skip[j] = false;
+    lneg[j] = kDead;
     if (p < L) {
       xoff[j] = lab[p] * 4;
       skip[j] = (p >= 1) && (lab[p - 1] != lab[p]);
+      lneg[j] = 0.0f;
     }
   }
   float* orow = out + t_first * sc.Sp;
@@ -347,57 +384,52 @@ ctc_lattice_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, 
   {
     const float* xrow = reinterpret_cast<const float*>(rows);
     const float2 cx = cxs[0];
-    float vmax = -CUDART_INF_F;
+    float vmax = kDead;
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-      const int p = pidx[j];
-      if (p <= L) {
-        const float vb = (p == 0) ? cx.y : -CUDART_INF_F;
-        float vl = -CUDART_INF_F;
-        if (p == 0 && L > 0) vl = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(xrow) + xoff[j]) * kLog2e;
-        *reinterpret_cast<float2*>(a0 + 2 * p) = make_float2(vb, vl);
-        if (p < L) *reinterpret_cast<float2*>(orow + 2 * p) = make_float2(vb, vl);
-        else orow[2 * p] = vb;
-        vmax = fmaxf(vmax, fmaxf(vb, vl));
-      }
+      const bool first = (p2[j] == 0);
+      const float vb = first ? cx.y : kDead;
+      float vl = kDead;
+      if (first && L > 0) vl = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(xrow) + xoff[j]) * kLog2e;
+      *reinterpret_cast<float2*>(a0 + p2[j]) = make_float2(vb, vl);
+      *reinterpret_cast<float2*>(orow + p2[j]) = make_float2(vb, vl);
+      vmax = fmaxf(vmax, fmaxf(vb, vl));
     }
     const int wmax = __reduce_max_sync(0xffffffffu, f2ord(vmax));
     if (lane == 0) wmx[warp] = wmax;
     orow += ostep;
     __syncthreads();
   }
-  int slot = 1 % R;
-  const unsigned char* xrow_b = rows + (size_t)slot * lay.row_stride;
+  const unsigned char* xrow_b = rows + (size_t)(1 % R) * lay.row_stride;
   const unsigned char* rows_end = rows + (size_t)R * lay.row_stride;
   int t = 1;
-  for (; t + 1 < Tn; t += 2) {                         // two steps per trip: static ping-pong buffers
-    lattice_step<P>(a0, a1, reinterpret_cast<const float*>(xrow_b), cxs[t & 3], orow, xoff, skip, pidx, L,
-                    wmx + (t & 3) * 32, warp, lane);
-    orow += ostep;
-    xrow_b += lay.row_stride;
-    if (xrow_b == rows_end) xrow_b = rows;
-    __syncthreads();
-    lattice_step<P>(a1, a0, reinterpret_cast<const float*>(xrow_b), cxs[(t + 1) & 3], orow, xoff, skip, pidx, L,
-                    wmx + ((t + 1) & 3) * 32, warp, lane);
-    orow += ostep;
-    xrow_b += lay.row_stride;
-    if (xrow_b == rows_end) xrow_b = rows;
-    __syncthreads();
+#define DAE_LAT_STEP(PREV, CUR, SLOT)                                                                        \
+  lattice_step<P>(PREV, CUR, reinterpret_cast<const float*>(xrow_b), cxs[SLOT], orow, xoff, skip, p2, lneg, \
+                  wmx + (SLOT) * 32, warp, lane);                                                            \
+  orow += ostep;                                                                                             \
+  xrow_b += lay.row_stride;                                                                                  \
+  if (xrow_b == rows_end) xrow_b = rows;                                                                     \
+  __syncthreads();
+  for (; t + 3 < Tn; t += 4) {                         // t = 1 (mod 4): static step slots and ping-pong buffers
+    DAE_LAT_STEP(a0, a1, 1)
+    DAE_LAT_STEP(a1, a0, 2)
+    DAE_LAT_STEP(a0, a1, 3)
+    DAE_LAT_STEP(a1, a0, 0)
   }
-  if (t < Tn) {                                        // odd tail (t is odd here: a0 -> a1)
-    lattice_step<P>(a0, a1, reinterpret_cast<const float*>(xrow_b), cxs[t & 3], orow, xoff, skip, pidx, L,
-                    wmx + (t & 3) * 32, warp, lane);
-    __syncthreads();
+  for (; t < Tn; ++t) {                                // up to three tail steps
+    if (t & 1) { DAE_LAT_STEP(a0, a1, t & 3) } else { DAE_LAT_STEP(a1, a0, t & 3) }
   }
+#undef DAE_LAT_STEP
 
   if (tid == 0) {
     const float* last = ((Tn - 1) & 1) ? a1 : a0;
     const float e1 = last[S - 1];
-    const float e2 = (S > 1) ? last[S - 2] : -CUDART_INF_F;
-    // total offset = off_a/off_b of the last processed frame, written by the producer before the last barrier
+    const float e2 = (S > 1) ? last[S - 2] : kDead;
+    // total offset = off_a/off_b of the last processed frame, written by the centring warp before the last barrier
     const double* offs = (dir ? sc.off_b : sc.off_a) + (int64_t)n * T;
     const double off_last = (Tn > 1) ? offs[dir ? 0 : (Tn - 1)] : 0.0;
-    const double ll2 = off_last + (double)lse2_2(e1, e2);
+    const float tail = lse2_n(e1, e2);
+    const double ll2 = (tail < -1.0e29f) ? -(double)CUDART_INF_F : off_last + (double)tail;   // dead: infeasible
     sc.ll2[dir * N + n] = ll2;
     if (dir == 0) nll[n] = (float)(-ll2 * kLn2d);
   }
@@ -507,7 +539,7 @@ static int ctc_check(const float* lp, int T, int N, int C, const int64_t* tgt, i
                      const int64_t* tgt_len, int blank, const void* scratch, size_t scratch_bytes) {
   if (!lp || !in_len || !tgt_len || T < 0 || N < 0 || C <= 0 || Lmax < 0 || blank < 0 || blank >= C) return DAE_E_BADARG;
   if (Lmax > 0 && !tgt) return DAE_E_BADARG;
-  if (Lmax + 1 > (dae::kLatThreads - 32) * dae::kMaxPairsPerThread) return DAE_E_TOOBIG;
+  if (Lmax + 1 > (dae::kLatThreads - 64) * dae::kMaxPairsPerThread) return DAE_E_TOOBIG;
   if (!scratch || scratch_bytes < dae_ctc_scratch_bytes(T, N, Lmax)) return DAE_E_SCRATCH;
   if ((reinterpret_cast<uintptr_t>(scratch) & 255u) != 0) return DAE_E_ALIGN;
   return 0;
@@ -523,15 +555,9 @@ extern "C" int dae_ctc_lattice(const float* lp, int64_t sT, int64_t sN, int T, i
   if (N == 0) return 0;
   CtcScratch sc;
   ctc_carve(sc, scratch, T, N, Lmax);
-  const int pairs = Lmax + 1;
-  constexpr int kMaxConsumers = kLatThreads - 32;        // one warp is the TMA producer
-  int P = (pairs + kMaxConsumers - 1) / kMaxConsumers;
-  P = P <= 1 ? 1 : (P <= 2 ? 2 : 4);
-  if (const char* e = getenv("DAE_CTC_PAIRS")) {         // tuning override (1, 2 or 4 pairs per thread)
-    const int q = atoi(e);
-    if ((q == 1 || q == 2 || q == 4) && (pairs + q - 1) / q <= kMaxConsumers) P = q;
-  }
-  int NT = (((pairs + P - 1) / P + 31) / 32) * 32 + 32;  // consumers + producer warp
+  int P, NTc;
+  lat_geometry(Lmax, P, NTc);
+  const int NT = NTc + 64;                               // consumers + two helper warps
   const LatSmem lay = lat_smem_layout(C, sc.Lp, sc.Sp, kLatSmemBudget);
   if (lay.stages < 2) return DAE_E_TOOBIG;
   const int vec = aligned16(lp) && (C % 4 == 0) && (sT % 4 == 0) && (sN % 4 == 0);

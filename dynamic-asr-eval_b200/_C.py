@@ -41,10 +41,12 @@ _PROTOS = {
     "dae_softdtw_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, ctypes.c_float,
                                 ctypes.c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dae_beam_scratch_bytes": (c_size_t, [c_int, c_int]),
+    "dae_ngram_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                 ctypes.c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dae_beam_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
                                 ctypes.c_float, ctypes.c_float, c_int, ctypes.c_float, ctypes.c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                ctypes.c_float, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int,
+                                ctypes.c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dae_stitch": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64,
                            c_void_p, c_void_p, c_void_p]),

@@ -29,6 +29,9 @@ struct DaeNgram {
   const int32_t* depth;
   int n_nodes, order, bos_state;
   float unk_lp;
+  // optional dense expansion of the context nodes (dae_ngram_expand): row[state*V + w] = log p(w | state),
+  // next[state*V + w] = successor state; NULL = walk the trie
+  const float* row; const int32_t* next; int V;
 };
 
 struct BeamRec {            // 40 bytes
@@ -72,7 +75,7 @@ __device__ __forceinline__ int lm_find(const DaeNgram& lm, int node, int w) {
   return -1;
 }
 // log p(w | state): longest context first, fp32 adds in that order (dae/ngram.py docstring).
-__device__ __forceinline__ float lm_score(const DaeNgram& lm, int state, int w) {
+__device__ __forceinline__ float lm_score_walk(const DaeNgram& lm, int state, int w) {
   float acc = 0.0f;
   int cur = state;
   for (;;) {
@@ -83,13 +86,32 @@ __device__ __forceinline__ float lm_score(const DaeNgram& lm, int state, int w) 
     cur = __ldg(lm.fail + cur);
   }
 }
-__device__ __forceinline__ int lm_next_state(const DaeNgram& lm, int state, int w) {
+__device__ __forceinline__ int lm_next_state_walk(const DaeNgram& lm, int state, int w) {
   int cur = state;
   for (;;) {
     const int c = lm_find(lm, cur, w);
     if (c >= 0 && __ldg(lm.depth + c) < lm.order) return c;
     if (cur == 0) return 0;
     cur = __ldg(lm.fail + cur);
+  }
+}
+
+__device__ __forceinline__ float lm_score(const DaeNgram& lm, int state, int w) {
+  return lm.row ? __ldg(lm.row + (size_t)state * lm.V + w) : lm_score_walk(lm, state, w);
+}
+__device__ __forceinline__ int lm_next_state(const DaeNgram& lm, int state, int w) {
+  return lm.next ? __ldg(lm.next + (size_t)state * lm.V + w) : lm_next_state_walk(lm, state, w);
+}
+
+// Dense expansion of the trie: one thread per (context node, token), same device functions as the search,
+// so the cached scores are bit-identical to a walk.
+__global__ void __launch_bounds__(256)
+ngram_expand_kernel(DaeNgram lm, int n_ctx, float* __restrict__ row, int32_t* __restrict__ next) {
+  const size_t n = (size_t)n_ctx * lm.V;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int node = (int)(i / lm.V), w = (int)(i - (size_t)node * lm.V);
+    row[i] = lm_score_walk(lm, node, w);
+    next[i] = lm_next_state_walk(lm, node, w);
   }
 }
 
@@ -107,6 +129,7 @@ __device__ __forceinline__ unsigned bt_hash(unsigned long long h, int len, int f
 
 struct BeamSmem {
   BeamRec beams[kMaxBeams];
+  BeamRec next_beams[kMaxBeams];            // next frame's beams, written at their rank
   int bt[kBtSlots];
   int top_idx[kMaxTop];
   float top_am[kMaxTop];
@@ -115,10 +138,11 @@ struct BeamSmem {
   int sv[kMaxCand];
   unsigned char c_lead[kMaxCand];
   float red_f[kBeamThreads / 32];
+  float red_g[kBeamThreads / 32];
   int red_i[kBeamThreads / 32];
   int warp_cnt[kBeamThreads / 32];
-  int ntop, n_sv, arena_used, error, n_new;
-  float thr, best;
+  int ntop, n_sv, arena_used, error, n_new, n_unflagged;
+  float thr, best, best_nb;
 };
 
 __device__ __forceinline__ int bt_lookup(const BeamSmem& S, unsigned long long h, int len, int flag) {
@@ -155,9 +179,10 @@ beam_search_kernel(BeamParams P) {
       r.hash = 0x1234567887654321ull; r.phash = 0; r.score = 0.0f; r.len = 0; r.last = -1; r.flag = 0;
       r.lmst = P.lm.bos_state; r.hist = -1;
       S.beams[0] = r;
-      nb_s = 1; pos_s = 0; S.arena_used = 0; S.error = 0;
+      nb_s = 1; pos_s = 0; S.arena_used = 0; S.error = 0; S.n_unflagged = 1;
     } else {
       nb_s = hdr->n_beams; pos_s = hdr->position; S.arena_used = hdr->arena_used; S.error = hdr->error;
+      S.n_unflagged = 1;                       // conservative until the next general frame recounts
     }
   }
   __syncthreads();
@@ -168,27 +193,73 @@ beam_search_kernel(BeamParams P) {
   int t = pos_s;
   const int t_end = min(seg_T, t + P.t_count);
 
+  // emission rows are double-buffered in smem: frame t+1 is requested (cp.async) while frame t is searched
+  float* rowbuf = reinterpret_cast<float*>(smem_raw + ((sizeof(BeamSmem) + 15) / 16) * 16);
+  const int Cpad = (P.C + 3) & ~3;
+  const bool row16 = (P.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.lp) & 15u) == 0);
+  auto request_row = [&](int tt, int buf) {
+    if (tt >= t_end) return;
+    const float* src = P.lp + (size_t)(seg_lo + tt) * P.C;
+    float* dst = rowbuf + buf * Cpad;
+    if (row16) {
+      for (int i = tid; i < (P.C >> 2); i += kBeamThreads)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + 4 * i)), "l"(src + 4 * i) : "memory");
+    } else {
+      for (int i = tid; i < P.C; i += kBeamThreads)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)), "l"(src + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  request_row(t, t & 1);
   for (; t < t_end && !S.error; ++t) {
-    const float* cur = P.lp + (size_t)(seg_lo + t) * P.C;
-    // ---- P0: frame maximum -> strict threshold (:225)
-    float m = -CUDART_INF_F;
-    for (int i = tid; i < P.C; i += kBeamThreads) m = fmaxf(m, __ldg(cur + i));
+    request_row(t + 1, (t + 1) & 1);
+    if (t + 1 < t_end) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                   // frame t's row is in smem for every thread
+    const float* cur = rowbuf + (t & 1) * Cpad;
+    // ---- P0: frame maximum -> strict threshold (:225); also the best non-blank candidate class
+    float m = -CUDART_INF_F, mnb = -CUDART_INF_F;
+    for (int i = tid; i < P.C; i += kBeamThreads) {
+      const float v = cur[i];
+      m = fmaxf(m, v);
+      if (i >= 1 && i < blank) mnb = fmaxf(mnb, v);
+    }
     m = warp_max(m);
-    if (lane == 0) S.red_f[warp] = m;
+    mnb = warp_max(mnb);
+    if (lane == 0) { S.red_f[warp] = m; S.red_g[warp] = mnb; }
     if (tid == 0) { S.ntop = 0; S.n_sv = 0; S.n_new = 0; }
     for (int i = tid; i < kBtSlots; i += kBeamThreads) S.bt[i] = -1;
     __syncthreads();
     if (tid == 0) {
-      float mm = S.red_f[0];
-      for (int w = 1; w < kBeamThreads / 32; ++w) mm = fmaxf(mm, S.red_f[w]);
+      float mm = S.red_f[0], mb = S.red_g[0];
+      for (int w = 1; w < kBeamThreads / 32; ++w) { mm = fmaxf(mm, S.red_f[w]); mb = fmaxf(mb, S.red_g[w]); }
       S.thr = __fadd_rn(mm, P.top_thr);
+      S.best_nb = mb;
     }
     __syncthreads();
     const float thr = S.thr;
+    // ---- fast path: blank is the only candidate class and every beam already ends in blank.  Then every
+    // candidate is "stay", no two candidates share a key, and adding one constant keeps the (stable) order:
+    // update the scores in place and cut the tail with the relative prune.
+    {
+      const float am_b = cur[blank];
+      if (am_b > thr && !(S.best_nb > thr) && S.n_unflagged == 0) {
+        float sc = 0.0f;
+        if (tid < nb) {
+          sc = __fadd_rn(__fadd_rn(am_b, S.beams[tid].score), P.blank_pen);
+          S.beams[tid].score = sc;
+        }
+        __syncthreads();
+        const float lim = P.has_prune ? __fsub_rn(S.beams[0].score, P.prune_val) : -CUDART_INF_F;
+        const int kept = __syncthreads_count(tid < nb && !(sc < lim));
+        nb = kept;                                   // scores are non-increasing: the kept beams are a prefix
+        continue;
+      }
+    }
     // ---- P1: ordered compaction of candidate classes 1..V
     for (int base_i = 1; base_i <= P.V; base_i += kBeamThreads) {
       const int i = base_i + tid;
-      const float v = (i <= P.V) ? __ldg(cur + i) : 0.0f;
+      const float v = (i <= P.V) ? cur[i] : 0.0f;
       const bool keep = (i <= P.V) && v > thr;
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
       if (lane == 0) S.warp_cnt[warp] = __popc(bal);
@@ -293,7 +364,9 @@ beam_search_kernel(BeamParams P) {
     __syncthreads();
     const int nsv = S.n_sv;
     const int nb_new = min(nsv, P.beam_width);
-    BeamRec* nxt = gbeams + (size_t)kMaxBeams;   // staging area in global memory for the next beam set
+    if (tid == 0) S.n_unflagged = 0;
+    __syncthreads();
+    BeamRec* nxt = S.next_beams;
     // rank by (score desc, creation index asc); rank < beam_width survives at position rank
     for (int j = tid; j < nsv; j += kBeamThreads) {
       const int c = S.sv[j];
@@ -329,6 +402,7 @@ beam_search_kernel(BeamParams P) {
           }
         }
         nxt[rank] = r;
+        if (r.flag == 0) atomicAdd(&S.n_unflagged, 1);
       }
     }
     __syncthreads();
@@ -377,7 +451,7 @@ extern "C" int dae_beam_search(const float* lp, const int32_t* seg_offsets, int 
                                float prune_less_than_val, int has_prune, float blank_penalty, float repetition_penalty,
                                const int32_t* lm_tok, const float* lm_logp, const float* lm_bo, const int32_t* lm_fail,
                                const int32_t* lm_cb, const int32_t* lm_depth, int lm_nodes, int lm_order,
-                               int lm_bos_state, float lm_unk_lp,
+                               int lm_bos_state, float lm_unk_lp, const float* lm_row, const int32_t* lm_next,
                                void* scratch, size_t scratch_bytes, int arena_cap,
                                int t_begin, int t_count, int finalize, int n_best, int out_cap,
                                float* out_score, int32_t* out_len, int32_t* out_flag, int32_t* out_tok,
@@ -397,14 +471,33 @@ extern "C" int dae_beam_search(const float* lp, const int32_t* seg_offsets, int 
   P.lp = lp; P.seg_off = seg_offsets; P.n_seg = n_seg; P.C = C; P.V = blank;
   P.beam_width = beam_width; P.alpha = alpha; P.beta = beta; P.top_thr = top_am_threshold;
   P.prune_val = prune_less_than_val; P.has_prune = has_prune; P.blank_pen = blank_penalty; P.rep_pen = repetition_penalty;
-  P.lm = DaeNgram{lm_tok, lm_logp, lm_bo, lm_fail, lm_cb, lm_depth, lm_nodes, lm_order, lm_bos_state, lm_unk_lp};
+  P.lm = DaeNgram{lm_tok, lm_logp, lm_bo, lm_fail, lm_cb, lm_depth, lm_nodes, lm_order, lm_bos_state, lm_unk_lp,
+                  lm_row, lm_next, blank};
   P.scratch = (unsigned char*)scratch; P.seg_stride = beam_seg_bytes(arena_cap); P.arena_cap = arena_cap;
   P.t_begin = t_begin; P.t_count = t_count; P.finalize = finalize; P.n_best = n_best; P.out_cap = out_cap;
   P.out_score = out_score; P.out_len = out_len; P.out_flag = out_flag; P.out_tok = out_tok; P.out_time = out_time;
   P.out_n = out_n;
-  const int smem = (int)sizeof(BeamSmem);
+  const int smem = (int)(((sizeof(BeamSmem) + 15) / 16) * 16 + 2 * (size_t)((C + 3) & ~3) * sizeof(float));
+  if (smem > 220 * 1024) return DAE_E_TOOBIG;
   DAE_CUDA(cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   beam_search_kernel<<<n_seg, kBeamThreads, smem, (cudaStream_t)stream>>>(P);
+  DAE_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int dae_ngram_expand(const int32_t* lm_tok, const float* lm_logp, const float* lm_bo, const int32_t* lm_fail,
+                                const int32_t* lm_cb, const int32_t* lm_depth, int lm_nodes, int lm_order, float lm_unk_lp,
+                                int vocab, int n_ctx, float* row, int32_t* next, void* stream) {
+  using namespace dae;
+  if (!lm_tok || !lm_logp || !lm_bo || !lm_fail || !lm_cb || !lm_depth || !row || !next || lm_nodes < 1 || lm_order < 1 ||
+      vocab < 1 || n_ctx < 0 || n_ctx > lm_nodes)
+    return DAE_E_BADARG;
+  if (n_ctx == 0) return 0;
+  DaeNgram lm{lm_tok, lm_logp, lm_bo, lm_fail, lm_cb, lm_depth, lm_nodes, lm_order, 0, lm_unk_lp, nullptr, nullptr, vocab};
+  const size_t n = (size_t)n_ctx * vocab;
+  size_t want = (n + 255) / 256;
+  const int grid = (int)(want < (size_t)kNumSMs * 16 ? want : (size_t)kNumSMs * 16);
+  ngram_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lm, n_ctx, row, next);
   DAE_LAUNCH_OK();
   return 0;
 }

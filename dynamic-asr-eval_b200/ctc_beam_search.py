@@ -40,7 +40,7 @@ class _Search:
 
     def __init__(self, log_probs, seg_offsets, lm, beam_width, alpha, beta, blank_id, blank_penalty,
                  repetition_penalty, top_am_threshold, prune_less_than_val, n_best=None, arena_per_frame=16,
-                 device=None):
+                 device=None, dense_lm=True):
         if not torch.cuda.is_available():
             raise _C.DaeError("beam search needs a CUDA device: there is no CPU path")
         if not isinstance(lm, NGramLM):
@@ -60,7 +60,10 @@ class _Search:
         self.n_seg = len(so) - 1
         self.max_T = max((b - a for a, b in zip(so[:-1], so[1:])), default=0)
         self.seg = torch.tensor(so, dtype=torch.int32, device=dev)
+        if lm.vocab_size != blank_id:
+            raise _C.DaeError(f"language model vocabulary ({lm.vocab_size}) must equal blank_id ({blank_id})")
         self.lm, self.arr = lm, lm.device_arrays(dev)
+        self.row, self.nxt = lm.dense_tables(dev) if dense_lm else (None, None)
         self.W, self.alpha, self.beta = int(beam_width), float(alpha), float(beta)
         self.blank, self.bpen, self.rpen = int(blank_id), float(blank_penalty), float(repetition_penalty)
         self.thr = float(top_am_threshold)
@@ -91,7 +94,8 @@ class _Search:
                 self.thr, float(self.prune) if self.prune is not None else 0.0, int(self.prune is not None),
                 self.bpen, self.rpen, a["tok"].data_ptr(), a["logp"].data_ptr(), a["bo"].data_ptr(),
                 a["fail"].data_ptr(), a["cb"].data_ptr(), a["depth"].data_ptr(), self.lm.n_nodes, self.lm.order,
-                self.lm.state_of([self.lm.bos_id]), float(self.lm.unk_lp), self.scratch.data_ptr(), self.nbytes,
+                self.lm.state_of([self.lm.bos_id]), float(self.lm.unk_lp), _C.ptr(self.row), _C.ptr(self.nxt),
+                self.scratch.data_ptr(), self.nbytes,
                 self.arena_cap, 1 if self.started else 0, int(n_frames), int(finalize), self.n_best, self.out_cap,
                 self.o_score.data_ptr(), self.o_len.data_ptr(), self.o_flag.data_ptr(), self.o_tok.data_ptr(),
                 self.o_time.data_ptr(), self.o_n.data_ptr(), _C.stream_ptr(self.dev))

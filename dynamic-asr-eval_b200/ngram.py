@@ -170,6 +170,29 @@ class NGramLM:
                               for k in ("tok", "logp", "bo", "depth", "fail", "cb")}
         return self._dev[key]
 
+    def dense_tables(self, device, max_bytes=2 << 30):
+        """Dense (row, next) expansion of the context nodes on ``device`` (dae_ngram_expand), or (None, None) when
+        n_ctx * vocab * 8 bytes would exceed ``max_bytes`` (large vocabularies keep walking the trie)."""
+        from . import _C
+        key = "dense:" + str(device)
+        if key not in self._dev:
+            n_ctx = int((self.depth < self.order).sum())           # nodes are ordered by depth: a prefix
+            V = self.vocab_size
+            if n_ctx * V * 8 > max_bytes:
+                self._dev[key] = (None, None)
+            else:
+                a = self.device_arrays(device)
+                row = torch.empty((n_ctx, V), dtype=torch.float32, device=device)
+                nxt = torch.empty((n_ctx, V), dtype=torch.int32, device=device)
+                with torch.cuda.device(device):
+                    rc = _C.lib().dae_ngram_expand(a["tok"].data_ptr(), a["logp"].data_ptr(), a["bo"].data_ptr(),
+                                                   a["fail"].data_ptr(), a["cb"].data_ptr(), a["depth"].data_ptr(),
+                                                   self.n_nodes, self.order, float(self.unk_lp), V, n_ctx,
+                                                   row.data_ptr(), nxt.data_ptr(), _C.stream_ptr(device))
+                _C.check(rc, "dae_ngram_expand")
+                self._dev[key] = (row, nxt)
+        return self._dev[key]
+
     # host-side state helpers (index arithmetic only; scoring happens on the device)
     def state_of(self, history):
         """Trie node of the longest suffix of ``history`` (at most order-1 tokens) that is a node."""

@@ -156,7 +156,8 @@ int dae_softdtw_bwd(const float* D, const float* R, const float* gout, int64_t g
  * lp           [total_T, C] fp32 log-probs, row stride C; blank must be C-1 (the class assumes
  *              blank_id == vocab_size, lib.py:64)
  * seg_offsets  [n_seg+1] int32 (device): segment g = rows seg_offsets[g] .. seg_offsets[g+1]
- * lm_*         flat trie arrays on the device (tok/logp/bo/fail/depth [lm_nodes], cb [lm_nodes+1])
+ * lm_*         flat trie arrays on the device (tok/logp/bo/fail/depth [lm_nodes], cb [lm_nodes+1]);
+ *              lm_row/lm_next: optional dense expansion from dae_ngram_expand (NULL = walk the trie)
  * scratch      dae_beam_scratch_bytes(n_seg, arena_cap) bytes, 256-aligned; holds the beams and the
  *              backpointer arena (arena_cap new-token entries per segment) and persists between
  *              calls, so a search can be advanced t_count frames at a time (BeamSearch.step()).
@@ -167,12 +168,18 @@ int dae_softdtw_bwd(const float* D, const float* R, const float* gout, int64_t g
  *              0, DAE_E_TOOBIG = more than 4096 candidates in one frame, DAE_E_SCRATCH = arena full).
  * ------------------------------------------------------------------------------------ */
 size_t dae_beam_scratch_bytes(int n_seg, int arena_cap);
+/* Dense expansion of the trie's context nodes (nodes 0..n_ctx-1, i.e. depth < order): row[s*vocab+w] =
+ * log p(w | state s), next[s*vocab+w] = successor state.  Same arithmetic as the in-search walk (bit-identical);
+ * trades n_ctx*vocab*8 bytes of HBM for one load per LM query.  vocab = number of LM tokens (= blank id). */
+int dae_ngram_expand(const int32_t* lm_tok, const float* lm_logp, const float* lm_bo, const int32_t* lm_fail,
+                     const int32_t* lm_cb, const int32_t* lm_depth, int lm_nodes, int lm_order, float lm_unk_lp,
+                     int vocab, int n_ctx, float* row, int32_t* next, void* stream);
 int dae_beam_search(const float* lp, const int32_t* seg_offsets, int n_seg, int C, int blank,
                     int beam_width, float alpha, float beta, float top_am_threshold,
                     float prune_less_than_val, int has_prune, float blank_penalty, float repetition_penalty,
                     const int32_t* lm_tok, const float* lm_logp, const float* lm_bo, const int32_t* lm_fail,
                     const int32_t* lm_cb, const int32_t* lm_depth, int lm_nodes, int lm_order,
-                    int lm_bos_state, float lm_unk_lp,
+                    int lm_bos_state, float lm_unk_lp, const float* lm_row, const int32_t* lm_next,
                     void* scratch, size_t scratch_bytes, int arena_cap,
                     int t_begin, int t_count, int finalize, int n_best, int out_cap,
                     float* out_score, int32_t* out_len, int32_t* out_flag, int32_t* out_tok,

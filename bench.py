@@ -167,6 +167,55 @@ def cpu_baseline_sample(frames):
                       f"stitch) through oracle/ref_loop.py with model and CTC on the CPU, {dt:.1f} s"}
 
 
+def aux_kernels(peak):
+    """The north star's other kernels at their BASELINE.json shapes (configs 3 and 4 + the whole-recording
+    greedy), timed alone with CUDA events and an L2 flush between iterations.  Reported next to the step's own
+    kernels; not part of `value`."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from kbench import Timer, peaky
+    from dae.ctc_beam_search import _Search
+    from dae.greedy import greedy_ids_device
+    from dae.ngram import NGramLM, read_arpa, write_synthetic_arpa
+    from dae.soft_dtw_cuda import softdtw_backward, softdtw_forward
+    from dae.standin import peaky_log_probs
+    tm = Timer()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    out = {}
+
+    def rec(name, shape, nbytes, med, extra=None):
+        out[name] = {"shape": shape, "algorithmic_bytes": nbytes, "ms": med * 1e3, "gbs": nbytes / med / 1e9,
+                     "frac_of_hbm_peak": nbytes / med / 1e9 / peak}
+        if extra:
+            out[name].update(extra)
+    lp = peaky(52000, 4096, 4095, g)
+    med, _ = tm.time(lambda: greedy_ids_device(lp, 4095), 10)
+    rec("greedy_collapse[52000x4096]", [52000, 4096], 52000 * 4096 * 4, med)
+    del lp
+    B, N, M = 8, 4096, 4096
+    x, y = torch.rand(B, N, 2, generator=g, device="cuda"), torch.rand(B, M, 2, generator=g, device="cuda")
+    D = ((x[:, :, None, :] - y[:, None, :, :]) ** 2).sum(-1).contiguous()
+    med, _ = tm.time(lambda: softdtw_forward(D, 1.0, 0.0), 6)
+    rec("softdtw_fwd[8x4096x4096]", [B, N, M], 2 * B * N * M * 4, med)
+    _, R, Dc = softdtw_forward(D, 1.0, 0.0)
+    go = torch.ones(B, device="cuda")
+    med, _ = tm.time(lambda: softdtw_backward(Dc, R, go, 1.0, 0.0), 6)
+    rec("softdtw_bwd[8x4096x4096]", [B, N, M], 3 * B * N * M * 4, med)
+    del D, R, Dc
+    V, T, nseg = 31, 180000, 360
+    arpa = "/tmp/dae_bench_4gram.arpa"
+    write_synthetic_arpa(arpa, V, order=4, counts=(None, 900, 200000, 800000), seed=4, fast=True)
+    order, grams = read_arpa(arpa)
+    lm = NGramLM(grams, order, V)
+    lpb = torch.from_numpy(peaky_log_probs(T, V + 1, V, 3, sharp=5.0)).cuda()
+    sr = _Search(lpb, [int(v) for v in np.linspace(0, T, nseg + 1)], lm, 100, 0.45, 1.53, V, 0.0, 0.0, -6, 3.17, n_best=1)
+    med, _ = tm.time(lambda: sr.run_all(), 3, warmup=1)
+    rec("beam_search[1h@50fps,V=32,beam=100,360 segments]", [T, V + 1, nseg], T * (V + 1) * 4, med,
+        {"frames_per_s": T / med, "audio_hours_per_s": T / 50 / 3600 / med, "lm_nodes": lm.n_nodes,
+         "lm_hbm_bytes": lm.nbytes() + 8 * int((lm.depth < lm.order).sum()) * V})
+    return out
+
+
 def run_dae(a, rank, world, local):
     import random
     import torch.distributed as dist
@@ -259,6 +308,7 @@ def run_dae(a, rank, world, local):
                 "peak_source": peak_src, "avg_launch_us": t_pair * 1e3,
                 "note": "N=1 lattice is a 2048-step dependent chain (latency-bound); see DESIGN.md"}
     cpu = cpu_baseline_sample(a.frames) if world == 1 else None
+    aux = aux_kernels(peak) if (world == 1 and not a.no_aux) else None
     spec_bytes = a.frames * 80 * 4
     line = {
         "metric": "audio-hours/sec dynamic-eval", "value": value, "unit": "audio-hours/s", "n_gpus": world,
@@ -270,6 +320,7 @@ def run_dae(a, rank, world, local):
                 "d2h_bytes_per_step": int(nwin * 4 * 700 + 4 * n_ids / max(a.steps, 1)),
                 "ms_per_step": t_e2e / a.steps * 1e3},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": table, "cpu_baseline": cpu,
+        "kernels_at_baseline_shapes": aux,
     }
     print(json.dumps(line), flush=True)
 
@@ -281,6 +332,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dae", choices=["dae", "reference"])
     ap.add_argument("--frames", type=int, default=120000, help="frames per synthetic recording (100 fps)")
+    ap.add_argument("--no-aux", dest="no_aux", action="store_true", help="skip the BASELINE-shape kernel table")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))

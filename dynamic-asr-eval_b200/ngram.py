@@ -28,7 +28,7 @@ import torch
 LN10 = math.log(10.0)
 
 
-def write_synthetic_arpa(path, vocab_size, order=4, counts=(None, 2000, 4000, 4000), seed=4, bos_id=0):
+def write_synthetic_arpa(path, vocab_size, order=4, counts=(None, 2000, 4000, 4000), seed=4, bos_id=0, fast=False):
     """Write a random but well-formed ARPA file (prefix- and suffix-closed) over token ids 1..vocab_size-1
     (words are decimal ids, ``<s>`` is the bos token).  counts[k-1] = number of k-grams (None = all unigrams)."""
     rng = random.Random(seed)
@@ -46,6 +46,13 @@ def write_synthetic_arpa(path, vocab_size, order=4, counts=(None, 2000, 4000, 40
             by_prefix.setdefault(g[:-1], []).append(g)
         want = counts[k - 1] if counts[k - 1] is not None else len(prev_keys)
         cur, tries = {}, 0
+        if fast:
+            # enumerate every admissible extension once and sample without replacement (benchmark-sized LMs;
+            # the rejection loop below is kept as the default because the golden fixtures were drawn with it)
+            space = [g + (h[-1],) for g in prev_keys for h in by_prefix.get(g[1:], ()) if h[-1] != bos_id]
+            for ng in (space if len(space) <= want else rng.sample(space, want)):
+                cur[ng] = (rng.uniform(-3.0, -0.05), rng.uniform(-1.0, -0.02) if k < order else None)
+            tries = want * 50
         while len(cur) < want and tries < want * 50:
             tries += 1
             g = rng.choice(prev_keys)

@@ -10,6 +10,7 @@ Shapes follow earnings_finetune/lcasr160rb1.yaml:1-29.
 import math
 import random
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -257,3 +258,20 @@ def build_model(vocab_size, model_cfg=None, device="cuda", seed=0):
     model = StandInSCConformer(vocab_size, **cfg)
     model.device = torch.device(device)
     return model.to(model.device).eval()
+
+
+def peaky_log_probs(T, C, blank, seed, p_blank=0.6, sharp=5.0, rng=None):
+    """Synthetic CTC posteriors: one dominant class per frame with runs, fp32 log-softmax."""
+    rng = np.random.default_rng(seed) if rng is None else rng
+    z = rng.standard_normal((T, C)).astype(np.float32)
+    cls = rng.integers(1, C - 1, size=T)
+    cls[rng.random(T) < p_blank] = blank
+    for t in range(1, T):
+        if rng.random() < 0.4:
+            cls[t] = cls[t - 1]
+    z[np.arange(T), cls] += sharp
+    second = rng.integers(1, C - 1, size=T)                # a competitor so the beam actually branches
+    z[np.arange(T), second] += sharp * rng.random(T).astype(np.float32)
+    z = z - z.max(-1, keepdims=True)
+    lse = np.log(np.exp(z.astype(np.float64)).sum(-1, keepdims=True))
+    return (z - lse).astype(np.float32)

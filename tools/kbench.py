@@ -157,11 +157,11 @@ def main():
 
     if want("beam"):
         import numpy as np
-        from oracle.beam_oracle import peaky_log_probs
+        from dae.standin import peaky_log_probs
         from dae.ctc_beam_search import _Search
         from dae.ngram import NGramLM, read_arpa, write_synthetic_arpa
         V = 31
-        write_synthetic_arpa("/tmp/kbench.arpa", V, order=4, counts=(None, 900, 200000, 800000), seed=4)
+        write_synthetic_arpa("/tmp/kbench.arpa", V, order=4, counts=(None, 900, 200000, 800000), seed=4, fast=True)
         order, grams = read_arpa("/tmp/kbench.arpa")
         lm = NGramLM(grams, order, V)
         T = 180000

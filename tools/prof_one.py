@@ -89,11 +89,11 @@ def main():
         torch.cuda.synchronize()
     elif a.what == "beam":
         import numpy as np
-        from oracle.beam_oracle import peaky_log_probs
+        from dae.standin import peaky_log_probs
         from dae.ctc_beam_search import _Search
         from dae.ngram import NGramLM, read_arpa, write_synthetic_arpa
         V, T, nseg = 31, 18000, 36
-        write_synthetic_arpa("/tmp/prof.arpa", V, order=4, counts=(None, 900, 20000, 80000), seed=4)
+        write_synthetic_arpa("/tmp/prof.arpa", V, order=4, counts=(None, 900, 20000, 80000), seed=4, fast=True)
         order, grams = read_arpa("/tmp/prof.arpa")
         lm = NGramLM(grams, order, V)
         lp = torch.from_numpy(peaky_log_probs(T, V + 1, V, 3, sharp=5.0)).cuda()

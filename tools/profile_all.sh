@@ -11,10 +11,10 @@ KRE='regex:ctc_|argmax_rows|collapse_kernel|specaug_|stitch_kernel|softdtw_|beam
 for fam in $FAMS; do
   timeout 300 python tools/prof_one.py $fam --reps 2 > $O/plain_$fam.log 2>&1 || { echo "plain run of $fam failed"; tail -5 $O/plain_$fam.log; exit 1; }
 done
-timeout 300 python bench.py --steps 1 --warmup 1 --frames 40000 > $O/plain_bench.log 2>&1 || { echo "plain bench failed"; tail -5 $O/plain_bench.log; exit 1; }
+timeout 300 python bench.py --steps 1 --warmup 1 --frames 40000 --no-aux > $O/plain_bench.log 2>&1 || { echo "plain bench failed"; tail -5 $O/plain_bench.log; exit 1; }
 # launch list of the bench command, dae kernels only: device time of every launch (cold-cache, serialised)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -c 400 --csv \
-    --log-file $O/launches_${TAG}.csv python bench.py --steps 1 --warmup 1 --frames 40000 > $O/ncu_bench.log 2>&1
+    --log-file $O/launches_${TAG}.csv python bench.py --steps 1 --warmup 1 --frames 40000 --no-aux > $O/ncu_bench.log 2>&1
 echo "launch list rc=$?"
 for fam in $FAMS; do
   timeout 420 ncu --set full --clock-control none --import-source on -k "$KRE" -c 4 -f -o $O/${fam}_${TAG} \

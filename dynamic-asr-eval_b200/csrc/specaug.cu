@@ -9,7 +9,6 @@ namespace dae {
 constexpr int kMaxBands = 32;
 constexpr int kMaxAug = 4;
 constexpr int kSumGrid = kNumSMs * 2;     // partial sums, one per CTA
-constexpr int kSumThreads = 256;
 
 struct BandSet {
   int n_aug, nf, nt;
@@ -17,108 +16,115 @@ struct BandSet {
   int2 t[kMaxAug][kMaxBands];
 };
 
-// Pass 1: fp64 partial sums in a fixed order (deterministic run to run).
-template <bool VEC>
-__global__ void __launch_bounds__(kSumThreads)
-specaug_sum_kernel(const float* __restrict__ x, int64_t sF, int F, int T, double* __restrict__ partials) {
-  __shared__ double wsum[kSumThreads / 32];
-  double acc = 0.0;
-  if (VEC) {
-    const int t4 = T >> 2;
-    const int64_t n4 = (int64_t)F * t4;
-    for (int64_t i = (int64_t)blockIdx.x * kSumThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kSumThreads) {
-      const int f = (int)(i / t4), c = (int)(i - (int64_t)f * t4);
-      const float4 v = *reinterpret_cast<const float4*>(x + f * sF + 4 * c);
-      acc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
-    }
-  } else {
-    const int64_t n = (int64_t)F * T;
-    for (int64_t i = (int64_t)blockIdx.x * kSumThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kSumThreads) {
-      const int f = (int)(i / T), c = (int)(i - (int64_t)f * T);
-      acc += (double)x[f * sF + c];
-    }
-  }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < kSumThreads / 32; ++w) s += wsum[w];
-    partials[blockIdx.x] = s;
-  }
-}
-
 __device__ __forceinline__ bool in_bands(const int2* b, int n, int i) {
   bool m = false;
   for (int k = 0; k < n; ++k) m |= (i >= b[k].x) & (i < b[k].y);
   return m;
 }
 
-// Pass 2: every CTA re-reduces the (L2-resident) partials in the same fixed order, then streams
-// x once and writes n_aug masked + n_clean verbatim copies.
+// One cooperative grid (co-resident CTAs) does both passes with a grid barrier in between.  Pass 1 reads x once, writes the clean copies and every unmasked element of the augmented
+// copies, and leaves a fp64 partial sum per CTA; after the barrier every CTA reduces the partials in the
+// same fixed order and writes the fill value into the masked elements of its own slice.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int expected) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*((volatile unsigned int*)counter) < expected) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256)
-specaug_apply_kernel(const float* __restrict__ x, int64_t sF, int F, int T, const double* __restrict__ partials,
-                     int zero_masking, int n_clean, const __grid_constant__ BandSet bands,
-                     float* __restrict__ out, float* __restrict__ mean_out) {
+specaug_fused_kernel(const float* __restrict__ x, int64_t sF, int F, int T, double* __restrict__ partials,
+                     unsigned int* __restrict__ counter, int zero_masking, int n_clean,
+                     const __grid_constant__ BandSet bands, float* __restrict__ out, float* __restrict__ mean_out) {
   __shared__ double red[256];
   __shared__ float fill_s;
+  const int64_t plane = (int64_t)F * T;
+  const int t4 = T >> 2;
+  const int64_t n_items = VEC ? (int64_t)F * t4 : plane;
+  const int64_t per = (n_items + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = (lo + per < n_items) ? lo + per : n_items;
+  double acc = 0.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+    if (VEC) {
+      const int f = (int)(i / t4), c = 4 * (int)(i - (int64_t)f * t4);
+      const float4 v = ld_stream4(x + f * sF + c);
+      acc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+      const int64_t o = (int64_t)f * T + c;
+      for (int a = 0; a < bands.n_aug; ++a) {
+        if (in_bands(bands.f[a], bands.nf, f)) continue;                       // whole row masked: pass 2
+        if (bands.nt == 0) { st_stream4(out + a * plane + o, v); continue; }
+        float* dst = out + a * plane + o;
+        if (!in_bands(bands.t[a], bands.nt, c)) dst[0] = v.x;
+        if (!in_bands(bands.t[a], bands.nt, c + 1)) dst[1] = v.y;
+        if (!in_bands(bands.t[a], bands.nt, c + 2)) dst[2] = v.z;
+        if (!in_bands(bands.t[a], bands.nt, c + 3)) dst[3] = v.w;
+      }
+      for (int k = 0; k < n_clean; ++k) st_stream4(out + (bands.n_aug + k) * plane + o, v);
+    } else {
+      const int f = (int)(i / T), c = (int)(i - (int64_t)f * T);
+      const float v = x[f * sF + c];
+      acc += (double)v;
+      for (int a = 0; a < bands.n_aug; ++a)
+        if (!(in_bands(bands.f[a], bands.nf, f) || in_bands(bands.t[a], bands.nt, c))) out[a * plane + i] = v;
+      for (int k = 0; k < n_clean; ++k) out[(bands.n_aug + k) * plane + i] = v;
+    }
+  }
+  float fill = 0.0f;
   if (!zero_masking) {
-    double s = 0.0;
-    for (int i = threadIdx.x; i < kSumGrid; i += 256) s += partials[i];
-    red[threadIdx.x] = s;
+    // CTA partial in a fixed order: deterministic run to run
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sacc += red[w];
+      partials[blockIdx.x] = sacc;
+    }
+    grid_barrier(counter, gridDim.x);
+    double sgl = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) sgl += __ldcg(partials + i);
+    red[threadIdx.x] = sgl;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
       if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
       __syncthreads();
     }
     if (threadIdx.x == 0) fill_s = (float)(red[0] / ((double)F * (double)T));
-  } else if (threadIdx.x == 0) {
-    fill_s = 0.0f;
+    __syncthreads();
+    fill = fill_s;
   }
-  __syncthreads();
-  const float fill = fill_s;
   if (mean_out && blockIdx.x == 0 && threadIdx.x == 0) *mean_out = fill;
-
-  const int64_t plane = (int64_t)F * T;
-  if (VEC) {
-    const int t4 = T >> 2;
-    const int64_t n4 = (int64_t)F * t4;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+  // pass 2: the masked elements of this CTA's slice
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+    if (VEC) {
       const int f = (int)(i / t4), c = 4 * (int)(i - (int64_t)f * t4);
-      const float4 v = ld_stream4(x + f * sF + c);
       const int64_t o = (int64_t)f * T + c;
       for (int a = 0; a < bands.n_aug; ++a) {
-        float4 w = v;
-        if (in_bands(bands.f[a], bands.nf, f)) {
-          w = make_float4(fill, fill, fill, fill);
-        } else if (bands.nt) {
-          if (in_bands(bands.t[a], bands.nt, c)) w.x = fill;
-          if (in_bands(bands.t[a], bands.nt, c + 1)) w.y = fill;
-          if (in_bands(bands.t[a], bands.nt, c + 2)) w.z = fill;
-          if (in_bands(bands.t[a], bands.nt, c + 3)) w.w = fill;
-        }
-        st_stream4(out + a * plane + o, w);
+        float* dst = out + a * plane + o;
+        if (in_bands(bands.f[a], bands.nf, f)) { st_stream4(dst, make_float4(fill, fill, fill, fill)); continue; }
+        if (bands.nt == 0) continue;
+        if (in_bands(bands.t[a], bands.nt, c)) dst[0] = fill;
+        if (in_bands(bands.t[a], bands.nt, c + 1)) dst[1] = fill;
+        if (in_bands(bands.t[a], bands.nt, c + 2)) dst[2] = fill;
+        if (in_bands(bands.t[a], bands.nt, c + 3)) dst[3] = fill;
       }
-      for (int k = 0; k < n_clean; ++k) st_stream4(out + (bands.n_aug + k) * plane + o, v);
-    }
-  } else {
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < plane; i += (int64_t)gridDim.x * 256) {
+    } else {
       const int f = (int)(i / T), c = (int)(i - (int64_t)f * T);
-      const float v = x[f * sF + c];
-      for (int a = 0; a < bands.n_aug; ++a) {
-        const bool m = in_bands(bands.f[a], bands.nf, f) || in_bands(bands.t[a], bands.nt, c);
-        out[a * plane + i] = m ? fill : v;
-      }
-      for (int k = 0; k < n_clean; ++k) out[(bands.n_aug + k) * plane + i] = v;
+      for (int a = 0; a < bands.n_aug; ++a)
+        if (in_bands(bands.f[a], bands.nf, f) || in_bands(bands.t[a], bands.nt, c)) out[a * plane + i] = fill;
     }
   }
 }
 
 }  // namespace dae
 
-extern "C" size_t dae_specaug_scratch_bytes(void) { return sizeof(double) * dae::kSumGrid; }
+extern "C" size_t dae_specaug_scratch_bytes(void) { return sizeof(double) * dae::kSumGrid + 64; }
 
 extern "C" int dae_specaug_repeat(const float* x, int64_t sF, int F, int T, const int32_t* fmask_host, int nf,
                                   const int32_t* tmask_host, int nt, int zero_masking, int n_aug, int n_clean,
@@ -138,18 +144,16 @@ extern "C" int dae_specaug_repeat(const float* x, int64_t sF, int F, int T, cons
   }
   const bool vec = aligned16(x) && aligned16(out) && (T % 4 == 0) && (sF % 4 == 0);
   const bool need_mean = !zero_masking && n_aug > 0;
-  if (need_mean) {
-    if (vec) specaug_sum_kernel<true><<<kSumGrid, kSumThreads, 0, st>>>(x, sF, F, T, (double*)partials);
-    else     specaug_sum_kernel<false><<<kSumGrid, kSumThreads, 0, st>>>(x, sF, F, T, (double*)partials);
-    DAE_LAUNCH_OK();
-  }
-  const int64_t work = vec ? (int64_t)F * (T / 4) : (int64_t)F * T;
-  int64_t want = (work + 255) / 256;
-  const int grid = (int)(want < (int64_t)kNumSMs * 8 ? (want > 0 ? want : 1) : (int64_t)kNumSMs * 8);
-  if (vec)
-    specaug_apply_kernel<true><<<grid, 256, 0, st>>>(x, sF, F, T, (const double*)partials, need_mean ? 0 : 1, n_clean, bs, out, mean_out);
-  else
-    specaug_apply_kernel<false><<<grid, 256, 0, st>>>(x, sF, F, T, (const double*)partials, need_mean ? 0 : 1, n_clean, bs, out, mean_out);
+  // one cooperative launch: partial sums live at partials[0 .. kSumGrid), the barrier counter after them
+  double* part = (double*)partials;
+  unsigned int* counter = partials ? (unsigned int*)(part + kSumGrid) : nullptr;
+  if (need_mean) DAE_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+  int zm = need_mean ? 0 : 1;
+  float* mo = mean_out;
+  void* args[] = {(void*)&x, (void*)&sF, (void*)&F, (void*)&T, (void*)&part, (void*)&counter, (void*)&zm,
+                  (void*)&n_clean, (void*)&bs, (void*)&out, (void*)&mo};
+  const void* fn = vec ? (const void*)specaug_fused_kernel<true> : (const void*)specaug_fused_kernel<false>;
+  DAE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(kSumGrid), dim3(256), args, 0, st));
   DAE_LAUNCH_OK();
   return 0;
 }

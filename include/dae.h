@@ -72,7 +72,8 @@ int dae_collapse_path(const int32_t* path, int B, int T, const int32_t* lengths,
  *          bands over the frequency / time axis, drawn by the caller's RNG (nf,nt <= 32,
  *          n_aug <= 4).
  * mask value = 0 if zero_masking else mean(x) (fp64 accumulation, fixed reduction order,
- *          rounded once to fp32).  partials: scratch of dae_specaug_scratch_bytes() bytes.
+ *          rounded once to fp32).  partials: scratch of dae_specaug_scratch_bytes() bytes (partial sums +
+ *          the counter of the grid barrier; reset by the call).  One cooperative launch: x is read once.
  * mean_out  [1] fp32 out (the fill value actually used), may be NULL.
  * ------------------------------------------------------------------------------------ */
 size_t dae_specaug_scratch_bytes(void);

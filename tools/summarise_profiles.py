@@ -80,14 +80,14 @@ def main():
             w.writerow({c: r.get(c, "") for c in cols})
     # traffic of the CTC pair (per launch, DRAM read+write)
     traffic = {}
-    lat = [r for r in all_rows if r["kernel"].startswith("ctc_lattice")]
-    grd = [r for r in all_rows if r["kernel"].startswith("ctc_grad")]
+    lat = [r for r in all_rows if "ctc_lattice" in r["kernel"]]
+    grd = [r for r in all_rows if "ctc_grad" in r["kernel"]]
     if lat and grd:
         tb = (lat[-1].get("dram_read_MB", 0) + lat[-1].get("dram_write_MB", 0) + grd[-1].get("dram_read_MB", 0) +
               grd[-1].get("dram_write_MB", 0)) * 1e6
         traffic["ctc_lattice+ctc_grad"] = tb
     for r in all_rows:
-        traffic.setdefault("per_kernel", {})[r["kernel"]] = (r.get("dram_read_MB", 0) + r.get("dram_write_MB", 0)) * 1e6
+        traffic.setdefault("per_kernel", {})[r["family"] + ":" + r["kernel"]] = (r.get("dram_read_MB", 0) + r.get("dram_write_MB", 0)) * 1e6
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     # launch list
     ll = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")

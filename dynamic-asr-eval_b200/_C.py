@@ -29,6 +29,8 @@ _PROTOS = {
     "dae_specaug_scratch_bytes": (c_size_t, []),
     "dae_specaug_repeat": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                    c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dae_cutout_scratch_bytes": (c_size_t, [c_int]),
+    "dae_cutout": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "dae_ctc_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dae_ctc_lattice": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
                                 c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -105,3 +105,50 @@ class SpecAugment(torch.nn.Module):
                                                 out[b].data_ptr(), scratch.data_ptr(), None, st)
                     _C.check(rc, "dae_specaug_repeat")
         return out[0] if squeeze else out
+
+
+CUTOUT_MODES = {"zero": 0, "mean": 1, "mean_recording": 2}
+
+
+def draw_cutout_rects(spec_n, n_freq, seq_len, num_rectangles=5, max_width=100, max_height=10, generator=None):
+    """Rectangle draw of lcasr/lib.py:391-401, same torch.randint order: widths, heights, start_x, start_y.
+    Returns int32 [n, 4] = (start_x, end_x, start_y, end_y)."""
+    ratio = spec_n / seq_len
+    n = int(num_rectangles * ratio)
+    widths = torch.randint(1, max_width, (n,), generator=generator)
+    heights = torch.randint(1, max_height, (n,), generator=generator)
+    sx = torch.randint(0, spec_n, (n,), generator=generator)
+    ex = (sx + widths).clamp(max=spec_n)
+    sy = torch.randint(0, n_freq, (n,), generator=generator)
+    ey = (sy + heights).clamp(max=n_freq)
+    return torch.stack([sx, ex, sy, ey], 1).to(torch.int32).contiguous()
+
+
+def cutout(spec, seq_len, cutout_val="mean", num_rectangles=5, max_width=100, max_height=10, rects=None):
+    """lcasr/lib.py:384-417 on the GPU, in place.  ``spec`` [1,F,T] (or [F,T]) fp32 CUDA.  ``rects`` overrides
+    the random draw (tests / replay)."""
+    if num_rectangles == 0:
+        return spec
+    _C.require_cuda(spec, "spec")
+    if cutout_val not in CUTOUT_MODES:
+        raise _C.DaeError(f"cutout_val must be one of {sorted(CUTOUT_MODES)}")
+    x = spec[0] if spec.dim() == 3 else spec
+    if spec.dim() == 3 and spec.shape[0] != 1:
+        raise _C.DaeError("cutout assumes a batch size of 1 (lcasr/lib.py:387)")
+    if x.dtype != torch.float32 or x.stride(1) != 1:
+        raise _C.DaeError("cutout needs an fp32 tensor with contiguous time axis")
+    F, T = x.shape
+    if rects is None:
+        rects = draw_cutout_rects(T, F, seq_len, num_rectangles, max_width, max_height)
+    rects = rects.to(torch.int32).contiguous().cpu()
+    n = int(rects.shape[0])
+    if n == 0:
+        return spec
+    lib = _C.lib()
+    nbytes = lib.dae_cutout_scratch_bytes(n)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device), prof.span("cutout", 0):
+        rc = lib.dae_cutout(x.data_ptr(), x.stride(0), F, T, rects.data_ptr(), n, CUTOUT_MODES[cutout_val],
+                            scratch.data_ptr(), nbytes, _C.stream_ptr(x.device))
+    _C.check(rc, "dae_cutout")
+    return spec

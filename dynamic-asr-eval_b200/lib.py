@@ -27,7 +27,7 @@ import torch
 import torch.nn as nn
 
 from . import _C
-from .augment import SpecAugment
+from .augment import SpecAugment, cutout
 from .ctc import CTCLoss
 from .greedy import GreedyCTCDecoder, greedy_ids_device
 from .optim import MADGRAD
@@ -179,8 +179,8 @@ def dynamic_eval_ctc_loss(
     lr_args = get_lr_args_from_args(args)
     frame_shuffle_args = get_frame_shuffle_config_from_args(args)
     cutout_args = get_cutout_params_from_args(args, seq_len)
-    if cutout_args['num_rectangles'] or any(k.startswith('entropy_augmentation_') and d[k] for k in d):
-        raise _C.DaeError("cutout / entropy_augmentation are not on the B200 hot path yet (SURVEY.md §8f-3)")
+    if d.get('entropy_augmentation_enabled', False):
+        raise _C.DaeError("entropy_augmentation is not on the B200 hot path (SURVEY.md §8f-3)")
     num_negatives = 1
 
     # parameter snapshot: on-device clone (lib.py:482-483 clones to the CPU; restore semantics are the same)
@@ -236,6 +236,8 @@ def dynamic_eval_ctc_loss(
                 audio_chunk[:num_negatives] = frame_shuffle(audio_chunk[:num_negatives], **frame_shuffle_args)
             if random_noise:
                 audio_chunk[:num_negatives] = add_random_noise(audio_chunk[:num_negatives], random_noise)
+            if cutout_args['num_rectangles']:
+                cutout(audio_chunk[:num_negatives], **cutout_args)      # in place, lib.py:544
             out = model(audio_signal=audio_chunk)
             post = out['final_posteriors']                  # [2, T', C] log-probs
             text, ids = _pseudo_targets(post[-1].detach(), blank, tokenizer, beam_search_fn, beams)

@@ -83,6 +83,19 @@ int dae_specaug_repeat(const float* x, int64_t sF, int F, int T,
                        float* out, void* partials, float* mean_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (f-3) cutout: rectangles of the augmented window overwritten in place.
+ * replaces: cutout() at lcasr/lib.py:384-417 (called at :544 on the augmented copy).
+ * x          [F,T] fp32 in place, row stride sF
+ * rects_host [n_rect][4] HOST int32 (start_x, end_x, start_y, end_y), half-open, x = time, y = frequency,
+ *            in the order the reference draws and fills them (the last rectangle wins where they overlap)
+ * mode       0 = zero, 1 = each rectangle's own mean (taken before any fill), 2 = mean of the whole window
+ * scratch    dae_cutout_scratch_bytes(n_rect) bytes, 256-aligned (device copy of the table + means)
+ * ------------------------------------------------------------------------------------ */
+size_t dae_cutout_scratch_bytes(int n_rect);
+int dae_cutout(float* x, int64_t sF, int F, int T, const int32_t* rects_host, int n_rect, int mode,
+               void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * (1) CTC loss + gradient (torch.nn.CTCLoss semantics, zero_infinity=False).
  * replaces: torch.nn.CTCLoss(blank, reduction='sum')(...) and its backward at
  *           lcasr/lib.py:492,575-579 (AWMC: :250,324-331; finetune: earnings_finetune/train.py:259).

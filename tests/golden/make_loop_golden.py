@@ -106,6 +106,13 @@ def main():
     out["ids_flat_awmc"] = np.array([i for e in tok.encoded for i in e], dtype=np.int64)
     out["ids_len_awmc"] = np.array([len(e) for e in tok.encoded], dtype=np.int64)
     print("awmc", logits.shape, len(tok.encoded))
+    # cutout (lib.py:384-417): reference function with a fixed torch seed; the rectangle table is re-drawn
+    # with the same seed by dae.augment.draw_cutout_rects in the tests
+    for mode in ("mean", "mean_recording", "zero"):
+        spec = toy_spec(3, 700).clone()
+        torch.manual_seed(77)
+        res = ref_lib.cutout(spec, seq_len=512, cutout_val=mode, num_rectangles=40, max_width=60, max_height=12)
+        out[f"cutout_{mode}"] = res[0].numpy().astype(np.float32)
     # chunk index vectors from the reference's prepare_chunks at the BASELINE window settings
     for spec_n in (6000, 120000, 360000, 415990):
         td, keys = ref_lib.prepare_chunks(torch.zeros(1, 1, spec_n), 16384, 14336)

@@ -280,3 +280,30 @@ def test_stitch_single_window_identity(cuda):
     lp = torch.randn(750, 129).log_softmax(-1)
     out, path = stitch_windows([lp.to(cuda)], [0], [6000], 0)
     np.testing.assert_allclose(out.cpu().numpy(), lp.numpy(), rtol=0, atol=2e-6)
+
+
+# ---------------------------------------------------------------- cutout
+@pytest.mark.parametrize("mode", ["mean", "mean_recording", "zero"])
+def test_cutout_matches_oracle(cuda, mode):
+    from dae.augment import cutout, draw_cutout_rects
+    from oracle import cutout_oracle
+    g = torch.Generator().manual_seed(5)
+    spec = torch.randn(1, 80, 3000, generator=g)
+    torch.manual_seed(9)
+    rects = draw_cutout_rects(3000, 80, 16384, num_rectangles=205 * 6, max_width=792, max_height=41)
+    assert len(rects) == int(205 * 6 * 3000 / 16384)
+    x = spec.to(cuda).clone()
+    out = cutout(x, 16384, cutout_val=mode, rects=rects)
+    assert out.data_ptr() == x.data_ptr()                                # in place, like the reference
+    ref = cutout_oracle.cutout(spec[0].numpy(), rects.tolist(), mode)
+    got = x[0].cpu().numpy()
+    untouched = ref == spec[0].numpy()
+    np.testing.assert_array_equal(got[untouched], spec[0].numpy()[untouched])  # only rectangles are written
+    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-6)              # fp64 means vs numpy fp32 pairwise means
+    # a strided window view (row stride != T) works too
+    big = torch.randn(1, 80, 5000, generator=g).to(cuda)
+    view = big[:, :, 1000:4000]
+    before = big.clone()
+    cutout(view, 16384, cutout_val="zero", rects=rects)
+    assert torch.equal(big[:, :, :1000], before[:, :, :1000]) and torch.equal(big[:, :, 4000:], before[:, :, 4000:])
+    assert (view[0].cpu().numpy() == 0).sum() > 0

@@ -57,6 +57,16 @@ def test_dynamic_eval_matches_oracle_loop(cuda, online):
     assert (greedy_oracle.argmax_rows(ld) == greedy_oracle.argmax_rows(lo)).mean() > 0.995
 
 
+def test_dynamic_eval_with_cutout_matches_oracle_loop(cuda):
+    """Secondary augmentation: cutout rectangles on the augmented copy, same RNG stream."""
+    (lo, ro, eo), (ld, rd, ed) = _run_pair(cuda, False, cutout_num_rectangles=30, cutout_max_width=60,
+                                          cutout_max_height=12, cutout_value='mean')
+    assert eo == ed
+    for a, b in zip(ro, rd):
+        assert abs(a["loss"] - b["loss"]) <= 1e-4 * abs(a["loss"])
+    np.testing.assert_allclose(np.exp(ld), np.exp(lo), rtol=2e-3, atol=1e-6)
+
+
 def test_dynamic_eval_epochs0_is_plain_inference(cuda):
     (lo, ro, _), (ld, rd, _) = _run_pair(cuda, False, epochs=0)
     assert ro == [] and rd == []

@@ -146,3 +146,22 @@ def test_stitch_oracle_small():
     np.testing.assert_allclose(out[0], wins[0][0], rtol=1e-6)
     exp_row5 = np.log((np.exp(wins[0][5]) + np.exp(wins[1][3]) + np.exp(wins[2][1])) / 3)
     np.testing.assert_allclose(out[5], exp_row5, rtol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["mean", "mean_recording", "zero"])
+def test_cutout_oracle_matches_reference(mode):
+    """Rectangle draw order + fill semantics vs the reference's own cutout() (golden, lib.py:384-417)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from toy import toy_spec
+    from dae.augment import draw_cutout_rects
+    from oracle import cutout_oracle
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loop_toy.npz"))[f"cutout_{mode}"]
+    spec = toy_spec(3, 700)[0].numpy()
+    torch.manual_seed(77)
+    rects = draw_cutout_rects(700, 80, 512, num_rectangles=40, max_width=60, max_height=12).tolist()
+    assert len(rects) == int(40 * 700 / 512)
+    out = cutout_oracle.cutout(spec, rects, mode)
+    np.testing.assert_allclose(out, gold, rtol=0, atol=1e-6)        # means: torch fp32 sum vs numpy pairwise
+    assert (out != spec).any()

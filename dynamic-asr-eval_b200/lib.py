@@ -163,8 +163,9 @@ def dynamic_eval_ctc_loss(
         output: str = "numpy",
 ):
     """lcasr/lib.py:450-640.  ``output``: 'numpy' (reference behaviour: [N,C] float32 log-probs on the
-    host), 'device' (same tensor left on the GPU) or 'greedy' (collapsed ids of the stitched
-    posteriors as a python list — what run_dynamic_eval_full.py:100 computes next)."""
+    host), 'device' (same tensor left on the GPU), 'greedy' (collapsed ids of the stitched posteriors as a
+    python list — what run_dynamic_eval_full.py:100 computes next) or 'params' (adapt only: the updated
+    parameters, no final pass / stitch)."""
     device = model.device
     if torch.device(device).type != "cuda":
         raise _C.DaeError("dae.lib.dynamic_eval needs the model on a CUDA device: there is no CPU path")
@@ -264,6 +265,15 @@ def dynamic_eval_ctc_loss(
             torch.cuda.synchronize(device)
             print(f'Epoch runtime: {time.perf_counter() - e0}')
 
+    if output == 'params':
+        # adapt-only (run_half_concat_eval.py:64-160 `adapt_on_concat_only`): no final pass, no stitch
+        updated_model_params = [p.clone().detach().cpu() for p in model.parameters()]
+        with torch.no_grad():
+            for p, p_orig, rg in zip(params, original, req_grad):
+                p.data = p_orig.data
+                p.requires_grad = rg
+        return updated_model_params
+
     f0 = time.perf_counter()
     if not online:
         model.eval()
@@ -326,6 +336,17 @@ def dynamic_eval_ctc_loss(
 
 
 dynamic_eval = dynamic_eval_ctc_loss
+
+
+def adapt_on_concat_only(args, model, concat_spec, tokenizer, beamsearch=None, adapt_overlap=None):
+    """lcasr/run_half_concat_eval.py:64-160: adapt on a (concatenated) spectrogram and return the updated
+    parameters (CPU clones) without building stitched logits; the model's own parameters are restored."""
+    if getattr(args, 'awmc', False):
+        _, updated = AWMC(args, model, concat_spec, args.seq_len, adapt_overlap, tokenizer, use_tqdm=False,
+                          beam_search_fn=beamsearch, return_params=True)
+        return updated
+    return dynamic_eval_ctc_loss(args, model, concat_spec, args.seq_len, adapt_overlap, tokenizer, use_tqdm=False,
+                                 beam_search_fn=beamsearch, output='params')
 
 
 class _EMA:

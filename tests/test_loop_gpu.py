@@ -163,3 +163,29 @@ def test_run_dynamic_eval_full_main_and_beamsearch(cuda, tmp_path):
     args.lm_eval_beams, args.lm_tta_beams, args.save_path = 5, 3, ""
     wer2 = r.main(args, model=model, tokenizer=tok, data=data[:1], normalize=lambda s: s, beamsearch=bs)
     assert np.isfinite(wer2)
+
+
+def test_adapt_on_concat_only_equals_return_params(cuda):
+    """run_half_concat_eval.py:64-160: the adapt-only pass yields the same parameters as return_params=True."""
+    from dae import lib
+    from dae.optim import MADGRAD
+    from dae.standin import SyntheticTokenizer
+    tok = SyntheticTokenizer(vocab_size=TOY["C"] - 1, seed=0)
+    spec = toy_spec(4, 2600)
+    outs = []
+    for mode in ("full", "adapt_only"):
+        model = ToyModel(TOY["C"], seed=3).to(cuda)
+        model.device = cuda
+        before = [p.detach().clone() for p in model.parameters()]
+        args = make_args(TOY_CONFIG, seq_len=1024, awmc=False, **dict(TOY["kwargs"], epochs=1))
+        random.seed(5)
+        torch.manual_seed(5)
+        if mode == "full":
+            _, params = lib.dynamic_eval(args, model, spec, 1024, 512, tok, use_tqdm=False, optim=MADGRAD,
+                                         return_params=True)
+        else:
+            params = lib.adapt_on_concat_only(args, model, spec, tok, adapt_overlap=512)
+        assert all(torch.equal(a, b) for a, b in zip(before, model.parameters()))
+        outs.append(params)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

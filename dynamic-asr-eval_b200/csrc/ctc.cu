@@ -158,7 +158,8 @@ __host__ __device__ inline LatSmem lat_smem_layout(int C, int Lp, int Sp, int ma
   m.rows = (int)align_up((size_t)m.a1 + (size_t)(Sp + 4) * 4, 128);
   m.row_stride = (int)align_up((size_t)C * 4, 128);
   int st = (max_bytes - m.rows) / m.row_stride;
-  m.stages = st > 16 ? 16 : st;
+  st = st > 16 ? 16 : st;
+  m.stages = st >= 4 ? (st / 4) * 4 : st;                // a multiple of four lets the consumer loop use static ring offsets
   m.total = m.rows + m.stages * m.row_stride;
   return m;
 }
@@ -400,24 +401,33 @@ ctc_lattice_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, 
     orow += ostep;
     __syncthreads();
   }
-  const unsigned char* xrow_b = rows + (size_t)(1 % R) * lay.row_stride;
-  const unsigned char* rows_end = rows + (size_t)R * lay.row_stride;
+  // Frames 1..3 (and the tail) take the generic path; the main loop handles four frames per trip starting at a
+  // frame t = 0 (mod 4), so the step slots, the ping-pong buffers and (because the ring depth is a multiple of
+  // four) the four ring rows of a trip are all compile-time offsets from one pointer.
+  const size_t rs = lay.row_stride;
   int t = 1;
-#define DAE_LAT_STEP(PREV, CUR, SLOT)                                                                        \
-  lattice_step<P>(PREV, CUR, reinterpret_cast<const float*>(xrow_b), cxs[SLOT], orow, xoff, skip, p2, lneg, \
-                  wmx + (SLOT) * 32, warp, lane);                                                            \
-  orow += ostep;                                                                                             \
-  xrow_b += lay.row_stride;                                                                                  \
-  if (xrow_b == rows_end) xrow_b = rows;                                                                     \
+#define DAE_LAT_STEP(PREV, CUR, SLOT, XROW)                                                               \
+  lattice_step<P>(PREV, CUR, reinterpret_cast<const float*>(XROW), cxs[SLOT], orow, xoff, skip, p2, lneg, \
+                  wmx + (SLOT) * 32, warp, lane);                                                          \
+  orow += ostep;                                                                                           \
   __syncthreads();
-  for (; t + 3 < Tn; t += 4) {                         // t = 1 (mod 4): static step slots and ping-pong buffers
-    DAE_LAT_STEP(a0, a1, 1)
-    DAE_LAT_STEP(a1, a0, 2)
-    DAE_LAT_STEP(a0, a1, 3)
-    DAE_LAT_STEP(a1, a0, 0)
+  for (; t < Tn && (t & 3) != 0; ++t) {                // head: frames 1, 2, 3
+    const unsigned char* xr = rows + (size_t)(t % R) * rs;
+    if (t & 1) { DAE_LAT_STEP(a0, a1, t & 3, xr) } else { DAE_LAT_STEP(a1, a0, t & 3, xr) }
   }
-  for (; t < Tn; ++t) {                                // up to three tail steps
-    if (t & 1) { DAE_LAT_STEP(a0, a1, t & 3) } else { DAE_LAT_STEP(a1, a0, t & 3) }
+  int sb = t % R;                                      // ring slot of frame t (a multiple of 4 from here on)
+  for (; t + 3 < Tn; t += 4) {
+    const unsigned char* xr = rows + (size_t)sb * rs;
+    DAE_LAT_STEP(a1, a0, 0, xr)
+    DAE_LAT_STEP(a0, a1, 1, xr + rs)
+    DAE_LAT_STEP(a1, a0, 2, xr + 2 * rs)
+    DAE_LAT_STEP(a0, a1, 3, xr + 3 * rs)
+    sb += 4;
+    if (sb == R) sb = 0;
+  }
+  for (; t < Tn; ++t) {                                // up to three tail frames
+    const unsigned char* xr = rows + (size_t)(t % R) * rs;
+    if (t & 1) { DAE_LAT_STEP(a0, a1, t & 3, xr) } else { DAE_LAT_STEP(a1, a0, t & 3, xr) }
   }
 #undef DAE_LAT_STEP
 
@@ -559,7 +569,7 @@ extern "C" int dae_ctc_lattice(const float* lp, int64_t sT, int64_t sN, int T, i
   lat_geometry(Lmax, P, NTc);
   const int NT = NTc + 64;                               // consumers + two helper warps
   const LatSmem lay = lat_smem_layout(C, sc.Lp, sc.Sp, kLatSmemBudget);
-  if (lay.stages < 2) return DAE_E_TOOBIG;
+  if (lay.stages < 4) return DAE_E_TOOBIG;
   const int vec = aligned16(lp) && (C % 4 == 0) && (sT % 4 == 0) && (sN % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
 #define DAE_LAT(PP) return launch_lattice<PP>(NT, lay, vec, st, N, lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, nll, sc)

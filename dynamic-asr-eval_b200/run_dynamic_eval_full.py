@@ -46,7 +46,7 @@ def main(args, model=None, tokenizer=None, data=None, normalize=None, beamsearch
     if data is None:
         from . import standin
         data = datasets_functions[args.dataset](args.split) if args.dataset in datasets_functions else \
-            standin.synthetic_recordings(args.dataset, tokenizer=tokenizer)
+            standin.synthetic_recordings(args.dataset, tokenizer=tokenizer, scale=args.__dict__.get('synthetic_scale', 1.0))
     normalize = normalize or _default_normalize()
     blank = model.decoder.num_classes - 1
     decoder = GreedyCTCDecoder(tokenizer=tokenizer, blank_id=blank)

@@ -136,8 +136,8 @@ def workload_config(a):
     return {"workload": f"dynamic eval of one synthetic Earnings22-shaped recording per step ({a.frames} frames = "
                         f"{a.frames / FPS / 60:.1f} min, 80-mel, seq {SEQ_LEN} overlap {OVERLAP}, "
                         f"{n_windows(a.frames)} windows, 1 epoch + final pass + stitch + greedy)",
-            "model": "stand-in lcasr160rb1 (6 layers, d=768, 6x128 heads, conv k=9, x8 subsampling, C=4096), fp32, "
-                     "random-init, PyTorch encoder (not the product)",
+            "standin_encoder": "lcasr160rb1-shaped (6 layers, d=768, 6x128 heads, conv k=9, x8 subsampling, C=4096), "
+                               "fp32, random-init, PyTorch (not the product)",
             "spec_augment": "6 freq masks x 34, 0 time masks", "optimizer": "MADGRAD lr 9e-5",
             "l2": "inputs larger than L2 (model weights 0.36 GB + activations stream through every step)",
             "parallelism": f"recordings sharded over {a.gpus} rank(s), one int64[5] all-reduce per step"}
@@ -279,7 +279,9 @@ def run_dae(a, rank, world, local):
     launches = _C.launch_count() - l0
     kern = prof.summary()
     prof.enable(False)
+    prof.reset()
     t_e2e, n_ids = timed(a.steps, True, a.warmup + a.steps)
+    h2d_step, d2h_step = prof.h2d_bytes // max(a.steps, 1), prof.d2h_bytes // max(a.steps, 1)
     clocks = sampler.stop()
 
     value = audio_h * a.steps * world / t_dev
@@ -309,16 +311,14 @@ def run_dae(a, rank, world, local):
                 "note": "N=1 lattice is a 2048-step dependent chain (latency-bound); see DESIGN.md"}
     cpu = cpu_baseline_sample(a.frames) if world == 1 else None
     aux = aux_kernels(peak) if (world == 1 and not a.no_aux) else None
-    spec_bytes = a.frames * 80 * 4
     line = {
         "metric": "audio-hours/sec dynamic-eval", "value": value, "unit": "audio-hours/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": t_dev / a.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (N(0,1) log-mel stand-in, random-init weights, calibrated blank prior)",
         "config": workload_config(a),
-        "e2e": {"value": e2e, "unit": "audio-hours/s", "h2d_bytes_per_step": spec_bytes + nwin * 8 * 700,
-                "d2h_bytes_per_step": int(nwin * 4 * 700 + 4 * n_ids / max(a.steps, 1)),
-                "ms_per_step": t_e2e / a.steps * 1e3},
+        "e2e": {"value": e2e, "unit": "audio-hours/s", "h2d_bytes_per_step": int(h2d_step),
+                "d2h_bytes_per_step": int(d2h_step), "ms_per_step": t_e2e / a.steps * 1e3},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": table, "cpu_baseline": cpu,
         "kernels_at_baseline_shapes": aux,
     }

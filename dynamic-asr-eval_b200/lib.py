@@ -26,7 +26,7 @@ from typing import Callable
 import torch
 import torch.nn as nn
 
-from . import _C
+from . import _C, prof
 from .augment import SpecAugment, cutout
 from .ctc import CTCLoss
 from .greedy import GreedyCTCDecoder, greedy_ids_device
@@ -140,6 +140,8 @@ def _pseudo_targets(lp_teacher, blank, tokenizer, beam_search_fn, beams):
     if beam_search_fn is None or beams == 0:
         _, ids, n = greedy_ids_device(lp_teacher, blank)
         k = int(n[0].item())                               # the one host sync of the step
+        prof.count_d2h(n)
+        prof.count_d2h(ids[0, :k])
         text = tokenizer.decode(ids[0, :k].tolist())
     else:
         bs = beam_search_fn(log_probs=lp_teacher.detach(), beam_width=beams)
@@ -216,6 +218,8 @@ def dynamic_eval_ctc_loss(
     # one H2D copy of the whole recording; windows are device views
     t0 = time.perf_counter()
     spec_dev = spec.to(device, non_blocking=True) if not spec.is_cuda else spec
+    if not spec.is_cuda:
+        prof.count_h2d(spec)
     if spec_dev.dtype != torch.float32:
         spec_dev = spec_dev.float()
     model.eval()                                            # don't update batchrenorm (lib.py:524)
@@ -245,8 +249,9 @@ def dynamic_eval_ctc_loss(
             if verbose:
                 noisy = GreedyCTCDecoder(tokenizer=tokenizer, blank_id=blank)(post[0].detach())
                 print(f'Pseudo targets: {text}\nNoisy predictions: {noisy}\n\n--\n')
-            pseudo = torch.tensor(ids, dtype=torch.long).unsqueeze(0).to(device, non_blocking=True) \
-                .repeat(num_negatives, 1)
+            pseudo_host = torch.tensor(ids, dtype=torch.long).unsqueeze(0)
+            prof.count_h2d(pseudo_host)
+            pseudo = pseudo_host.to(device, non_blocking=True).repeat(num_negatives, 1)
             augmented_outs = post[:num_negatives]
             N, B = augmented_outs.shape[1], augmented_outs.shape[0]
             total_tokens_in_loss = N * B
@@ -319,12 +324,15 @@ def dynamic_eval_ctc_loss(
             p.requires_grad = rg
 
     if output == 'numpy':
+        prof.count_d2h(logits)
         result = logits.cpu().numpy()
     elif output == 'device':
         result = logits
     elif output == 'greedy':
         from .greedy import collapse_path_device
         result = collapse_path_device(path, blank)
+        prof.h2d_bytes += 0
+        prof.d2h_bytes += 4 * len(result) + 4
     else:
         raise ValueError(f"unknown output mode {output!r}")
     if print_runtimes:

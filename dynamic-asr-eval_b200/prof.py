@@ -10,6 +10,8 @@ from collections import defaultdict
 import torch
 
 _enabled = False
+h2d_bytes = 0          # bytes the dae host code copied host->device / device->host since reset()
+d2h_bytes = 0
 _records = defaultdict(list)     # name -> [(start_event, end_event, nbytes)]
 
 
@@ -19,7 +21,20 @@ def enable(flag=True):
 
 
 def reset():
+    global h2d_bytes, d2h_bytes
     _records.clear()
+    h2d_bytes = 0
+    d2h_bytes = 0
+
+
+def count_h2d(t):
+    global h2d_bytes
+    h2d_bytes += t.numel() * t.element_size()
+
+
+def count_d2h(t):
+    global d2h_bytes
+    d2h_bytes += t.numel() * t.element_size()
 
 
 @contextlib.contextmanager

@@ -262,7 +262,7 @@ def dynamic_eval_ctc_loss(
             loss.backward()
             optimizer.step()
             if d.get('_record_steps', False):
-                step_log.append({'key': i, 'ids': ids, 'loss': float(loss.item())})
+                step_log.append({'key': i, 'ids': ids, 'loss': loss.detach()})   # no sync here
             if online:
                 kept[i] = (post[-1].detach(), u_len)
         tm.add('adapt', time.perf_counter() - e0)
@@ -339,6 +339,8 @@ def dynamic_eval_ctc_loss(
         torch.cuda.synchronize(device)
         print('dae runtimes:', {k: round(v, 4) for k, v in tm.t.items()})
     if d.get('_record_steps', False):
+        for r in step_log:
+            r['loss'] = float(r['loss'])
         args.__dict__['_step_log'] = step_log
     return result if not return_params else (result, updated_model_params)
 

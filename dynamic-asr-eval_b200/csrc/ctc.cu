@@ -14,85 +14,9 @@
 //   ctc_grad_kernel    : one CTA per (t, n) row: dense exp(lp) minus the occupancy of the
 //                        classes that occur in the label sequence.  Pure streaming.
 #include <cstdlib>
-#include "common.cuh"
+#include "ctc_shared.cuh"
 
 namespace dae {
-
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr double kLn2d = 0.69314718055994530942;
-constexpr int kLatThreads = 1024;
-constexpr int kMaxPairsPerThread = 4;             // Lmax + 1 <= 4096 label/blank state pairs
-constexpr int kLatSmemBudget = 200 * 1024;        // dynamic smem for labels + lattice rows + emission ring
-
-struct CtcScratch {           // carved out of the caller's scratch buffer
-  float* alpha;               // [N][T][Sp]  centred, log2 units
-  float* beta_rev;            // [N][T][Sp]  beta stored at reversed state index S-1-s
-  int32_t* next_same;         // [N][Lp]  next label position with the same class, -1 = none
-  int32_t* leader;            // [N][Lp]  1 if first occurrence of its class
-  double* off_a;              // [N][T]   alpha_t(s) = alpha[t][s] + off_a[t]   (log2 units)
-  double* off_b;              // [N][T]   beta_t(s)  = beta_rev[t][S-1-s] + off_b[t]
-  double* ll2;                // [4][N]   log2-likelihood from the alpha CTA, the beta CTA, then debug totals
-  int Sp, Lp;
-};
-
-__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-// Thread geometry of the lattice kernel: P state pairs per consumer thread, NTc consumer threads.
-// Every consumer thread owns real or dummy pairs, so lattice rows are 2*NTc*P floats wide.
-static inline void lat_geometry(int Lmax, int& P, int& NTc) {
-  constexpr int kMaxConsumers = kLatThreads - 64;        // two helper warps: centring + TMA
-  const int pairs = Lmax + 1;
-  P = (pairs + kMaxConsumers - 1) / kMaxConsumers;
-  P = P <= 1 ? 1 : (P <= 2 ? 2 : 4);
-  static const int forced = [] { const char* e = getenv("DAE_CTC_PAIRS"); return e ? atoi(e) : 0; }();
-  if ((forced == 1 || forced == 2 || forced == 4) && (pairs + forced - 1) / forced <= kMaxConsumers) P = forced;
-  NTc = (((pairs + P - 1) / P + 31) / 32) * 32;
-}
-
-static inline size_t ctc_carve(CtcScratch& s, void* base, int T, int N, int Lmax) {
-  int P_, NTc_;
-  lat_geometry(Lmax, P_, NTc_);
-  s.Sp = 2 * NTc_ * P_;
-  s.Lp = (int)align_up((size_t)(Lmax > 0 ? Lmax : 1), 4);
-  char* p = (char*)base;
-  size_t off = 0;
-  const size_t lat = align_up((size_t)N * T * s.Sp * sizeof(float), 256);
-  s.alpha = (float*)(p + off); off += lat;
-  s.beta_rev = (float*)(p + off); off += lat;
-  const size_t lab = align_up((size_t)N * s.Lp * sizeof(int32_t), 256);
-  s.next_same = (int32_t*)(p + off); off += lab;
-  s.leader = (int32_t*)(p + off); off += lab;
-  const size_t offs = align_up((size_t)N * T * sizeof(double), 256);
-  s.off_a = (double*)(p + off); off += offs;
-  s.off_b = (double*)(p + off); off += offs;
-  s.ll2 = (double*)(p + off); off += align_up((size_t)4 * N * sizeof(double), 256);
-  return off;
-}
-
-__device__ __forceinline__ float fast_ex2(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float fast_lg2(float x) {
-  float r;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-// log2(2^a + 2^b + 2^c) with 3 MUFU ops: the largest term contributes exactly 1.
-// -inf inputs allowed; all -inf -> -inf.
-__device__ __forceinline__ float lse3_2(float a, float b, float c) {
-  const float lo = fminf(a, b), hi = fmaxf(a, b);
-  const float m = fmaxf(hi, c), mid = fminf(hi, c);
-  if (m == -CUDART_INF_F) return m;
-  return m + fast_lg2(1.0f + fast_ex2(mid - m) + fast_ex2(lo - m));
-}
-// Order-preserving float <-> int map so a warp max can use redux.sync / smem atomicMax.
-__device__ __forceinline__ int f2ord(float f) {
-  const int i = __float_as_int(f);
-  return i ^ ((i >> 31) & 0x7fffffff);
-}
-__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
 // ---- mbarrier / bulk-copy (TMA) helpers -------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -123,25 +47,6 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// log2(2^a + 2^b), 2 MUFU ops.
-__device__ __forceinline__ float lse2_2(float a, float b) {
-  const float m = fmaxf(a, b), lo = fminf(a, b);
-  if (m == -CUDART_INF_F) return m;
-  return m + fast_lg2(1.0f + fast_ex2(lo - m));
-}
-// Branch-free variants for the lattice: dead states hold the finite sentinel kDead instead of -inf
-// (kDead + anything finite == kDead in fp32, and kDead - kDead == 0, so no NaN can appear).
-constexpr float kDead = -1.0e30f;
-__device__ __forceinline__ float lse2_n(float a, float b) {
-  const float m = fmaxf(a, b), lo = fminf(a, b);
-  return m + fast_lg2(1.0f + fast_ex2(lo - m));
-}
-__device__ __forceinline__ float lse3_n(float a, float b, float c) {
-  const float lo = fminf(a, b), hi = fmaxf(a, b);
-  const float m = fmaxf(hi, c), mid = fminf(hi, c);
-  return m + fast_lg2(1.0f + fast_ex2(mid - m) + fast_ex2(lo - m));
 }
 
 struct LatSmem {              // byte offsets into dynamic shared memory (host and device agree)
@@ -565,6 +470,9 @@ extern "C" int dae_ctc_lattice(const float* lp, int64_t sT, int64_t sN, int T, i
   if (N == 0) return 0;
   CtcScratch sc;
   ctc_carve(sc, scratch, T, N, Lmax);
+  if (sc.xfer)                                           // few samples, many frames: spread the time axis over the GPU
+    return ctc_blocked_lattice(lp, sT, sN, T, N, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, nll, sc,
+                               (cudaStream_t)stream);
   int P, NTc;
   lat_geometry(Lmax, P, NTc);
   const int NT = NTc + 64;                               // consumers + two helper warps

@@ -112,6 +112,14 @@ def test_specaug_plain_call_and_determinism(cuda):
 
 
 # ---------------------------------------------------------------- CTC
+@pytest.fixture(params=["chain", "blocked"])
+def ctc_path(request, monkeypatch):
+    """Both lattice implementations behind dae_ctc_lattice: the per-frame chain (ctc.cu) and the time-blocked
+    scan (ctc_blocked.cu); DAE_CTC_BLOCKED forces one or the other regardless of shape."""
+    monkeypatch.setenv("DAE_CTC_BLOCKED", "1" if request.param == "blocked" else "0")
+    return request.param
+
+
 def _ctc_case(T, N, C, Lmax, seed, ragged=True, peaky=False):
     g = torch.Generator().manual_seed(seed)
     blank = C - 1
@@ -140,7 +148,7 @@ def _assert_ctc_grad_close(got, ref, lp64, g):
 
 @pytest.mark.parametrize("T,N,C,Lmax", [(40, 2, 7, 9), (200, 3, 129, 40), (512, 1, 4096, 150), (64, 4, 32, 0),
                                         (300, 2, 50, 149), (33, 1, 5, 1)])
-def test_ctc_matches_fp64_oracle(cuda, T, N, C, Lmax):
+def test_ctc_matches_fp64_oracle(cuda, T, N, C, Lmax, ctc_path):
     from dae.ctc import CTCLoss
     lp, tg, il, tl, blank = _ctc_case(T, N, C, Lmax, seed=T + N)
     if Lmax == 0:
@@ -169,7 +177,7 @@ def _teacher_student(T, C, g, noise):
     return torch.stack([student_logits.log_softmax(-1), teacher_logits.log_softmax(-1)])
 
 
-def test_ctc_hot_path_shape_vs_torch(cuda):
+def test_ctc_hot_path_shape_vs_torch(cuda, ctc_path):
     """cfg2 shape: lp is the non-contiguous view out[:1].transpose(0,1) of [2,2048,4096] (lib.py:570-575)."""
     from dae.ctc import CTCLoss
     T, C = 2048, 4096
@@ -199,7 +207,7 @@ def test_ctc_hot_path_shape_vs_torch(cuda):
     assert err_dae <= err_torch + 1e-9
 
 
-def test_ctc_mismatched_labels_vs_fp64(cuda):
+def test_ctc_mismatched_labels_vs_fp64(cuda, ctc_path):
     """Adversarial: labels unrelated to the posteriors, so the alignment runs through states ~2^-1000 below
     the per-frame maximum.  fp32 log-space keeps ~1e-3 there (documented in DESIGN.md); torch fp32 is worse."""
     from dae.ctc import CTCLoss
@@ -220,7 +228,7 @@ def test_ctc_mismatched_labels_vs_fp64(cuda):
     assert np.abs(got - grad).max() <= np.abs(y.grad.cpu().numpy() - grad).max() + 1e-9
 
 
-def test_ctc_reductions_and_infeasible(cuda):
+def test_ctc_reductions_and_infeasible(cuda, ctc_path):
     from dae.ctc import CTCLoss, ctc_loss
     lp, tg, il, tl, blank = _ctc_case(50, 3, 11, 8, seed=9)
     x = lp.to(cuda)
@@ -234,7 +242,7 @@ def test_ctc_reductions_and_infeasible(cuda):
     assert torch.isinf(bad) and bad > 0
 
 
-def test_ctc_large_magnitude_precision(cuda):
+def test_ctc_large_magnitude_precision(cuda, ctc_path):
     """Random logits, |log-likelihood| ~ 1e4 and the alignment far below the per-frame maximum: the centred
     fp32 lattice keeps the loss to 1e-5 and the gradient to ~1e-3 of its scale (DESIGN.md "CTC accuracy");
     torch's uncentred fp32 kernel is an order of magnitude further from fp64."""

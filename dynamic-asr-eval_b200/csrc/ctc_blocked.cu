@@ -11,7 +11,7 @@
 //   2. ctc_boundary_kernel  the only sequential part, T/K steps: boundary vectors
 //                           alpha_end(b)[s'] = LSE_d X_b[d][s'-d] + alpha_end(b-1)[s'-d]   and, with the same
 //                           bands read the other way, betahat_start(b)[s] = LSE_d X_b[d][s] + betahat_start(b+1)[s+d].
-//                           States are split into 128-state regions, one CTA each; a region only needs the last
+//                           States are split into 64-state regions, one CTA each; a region only needs the last
 //                           2K values of the region below it, handed over through tagged 8-byte words in global
 //                           memory (tag in the data, no fences), so regions run as a skewed pipeline.
 //   3. ctc_fill_kernel      every (block, direction) in parallel: K ordinary lattice steps from the block's
@@ -94,6 +94,7 @@ ctc_xfer_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, con
   constexpr int W = 2 * K + 1, EW = kXferTile + 2 * K;
   __shared__ float es[K][EW];                    // emission (log2) of state s0+j at frame t0+k
   __shared__ unsigned char skp[EW];              // 1: state s0+j may be entered from s0+j-2
+  __shared__ __align__(16) float outs[kXferTile * W];
   const int b = blockIdx.x, s0 = blockIdx.y * kXferTile, n = blockIdx.z, tid = threadIdx.x;
   int Tn, L;
   clamp_lengths(in_len, tgt_len, n, T, Lmax, Tn, L);
@@ -126,31 +127,48 @@ ctc_xfer_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, con
   for (int j = 1; j < W; ++j) v[j] = kDead;
   if (par == 0) xfer_steps<K, 0>(v, &es[0][0], EW, skp, jl, kb);
   else          xfer_steps<K, 1>(v, &es[0][0], EW, skp, jl, kb);
-  const int s = s0 + jl;
-  if (s < sc.Sq) {
-    float* out = sc.xfer + ((size_t)(n * sc.nblk + b) * W) * sc.Sq + s;
+  // bands leave as rows [source][d] (what the boundary scan bulk-copies), staged so the stores are 128-bit
+  __syncthreads();
 #pragma unroll
-    for (int d = 0; d < W; ++d) out[(size_t)d * sc.Sq] = v[d];
-  }
+  for (int d = 0; d < W; ++d) outs[jl * W + d] = v[d];
+  __syncthreads();
+  const int ncols = min(kXferTile, sc.Sq - s0);
+  float4* dst = reinterpret_cast<float4*>(sc.xfer + ((size_t)(n * sc.nblk + b) * sc.Sq + s0) * W);
+  const float4* src = reinterpret_cast<const float4*>(outs);
+  for (int i = tid; i < ncols * W / 4; i += kXferTile) dst[i] = src[i];
 }
 
 // ------------------------------------------------------------------------------------------ 2. boundary scan
 constexpr int kBndStages = 4;                     // transfer-band prefetch depth (steps)
+constexpr int kTermsPerThread = kBlkK + 1;        // two threads share the 2K+1 terms of a destination state
+constexpr int kBndThreads = 2 * kRegion + 96;     // consumers + band-prefetch, hand-over and frame warps
 
 // grid (G, 2, N): region g of direction dir (0 alpha, 1 beta in reversed state order u = S-1-s) of sample n.
-// 128 consumer threads (one destination state each) + one helper warp (offset bookkeeping, halo hand-over).
+// Two consumer threads per destination state and three helper warps, all meeting at one barrier per step:
+//   tma   warp: keeps kBndStages band chunks in flight (one TMA bulk copy per step) and waits for the next
+//               step's chunk before the step barrier, so consumers never poll an mbarrier;
+//   halo  warp: fetches the 2K values (and the frame) the region below produced for the same vector; the word
+//               of the next step is requested a step ahead so its L2 round trip stays off the critical path;
+//   frame warp: chooses the fp64 frame of reference of the vector two steps ahead and publishes it.
+// Halo values stay relative to the lower region's frame and are shifted when used.
 template <int K>
-__global__ void __launch_bounds__(kRegion + 32)
+__global__ void __launch_bounds__(kBndThreads)
 ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len,
                     float* __restrict__ nll, CtcScratch sc) {
-  constexpr int W = 2 * K + 1, H = 2 * K;
-  __shared__ float buf[2][H + kRegion];          // [halo of the region below | own region]
-  __shared__ float xs[kBndStages][W][kRegion];   // transfer bands of the next steps, one column per consumer
-  __shared__ int wmx[2][kRegion / 32];           // per-warp maxima of the own region of each buffer
-  __shared__ double off_s;
+  constexpr int W = 2 * K + 1, H = 2 * K, CH = (kRegion + H) * W;
+  __shared__ __align__(128) float xs[kBndStages][CH];   // band rows of the states this region reads, per step
+  __shared__ float buf[2][H + kRegion + 1];             // [halo of the region below (raw) | own region | dead cell]
+  __shared__ double hoff[2];                            // offset the halo values of each buffer are relative to
+  __shared__ int hmaxs[2];                              // their maximum (order-preserving int)
+  __shared__ float oshift[2];                           // per step: shift of own values into the new frame
+  __shared__ double Fd[2];                              // per step: the new frame itself
+  __shared__ int wmx[2][2 * kRegion / 32];              // per-warp maxima of the own region of each buffer
+  __shared__ uint64_t full[kBndStages];
   const int g = blockIdx.x, dir = blockIdx.y, n = blockIdx.z, N = gridDim.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool helper = tid >= kRegion;
+  const bool consumer = tid < 2 * kRegion;
+  const bool tma_warp = warp == 2 * kRegion / 32, halo_warp = warp == 2 * kRegion / 32 + 1,
+             frame_warp = warp == 2 * kRegion / 32 + 2;
   int Tn, L;
   clamp_lengths(in_len, tgt_len, n, T, Lmax, Tn, L);
   const int S = 2 * L + 1;
@@ -168,121 +186,255 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
   float* brow0 = sc.bound + vec0 * Sq;
   double* boff0 = sc.boff + vec0 * G;
   int2* halo0 = sc.halo + vec0 * G * kHaloWords;
-  const float* xf0 = sc.xfer + (size_t)n * sc.nblk * W * Sq;
-  const int u = g * kRegion + (tid & (kRegion - 1));
+  const float* xf0 = sc.xfer + (size_t)n * sc.nblk * Sq * W;
+  const int u0 = g * kRegion;
+  const int i = (tid >> 1) & (kRegion - 1), h = tid & 1;
+  const int u = u0 + i;
 
+  // Band rows this region reads each step, as one contiguous chunk of xfer[b]:
+  //   alpha: sources u0-H .. u0+R-1 (region 0 has no sources below 0: its first H rows in smem stay dead);
+  //   beta : rows of s = S-1-u for the region's u, i.e. s_hi-R+1 .. s_hi, clipped at 0, start aligned to 4 rows.
+  int col0, ncols, dst_off;
+  if (dir == 0) {
+    col0 = g > 0 ? u0 - H : 0;
+    ncols = g > 0 ? kRegion + H : kRegion;
+    dst_off = g > 0 ? 0 : H * W;
+  } else {
+    const int s_hi = S - 1 - u0;
+    const int s_lo = max(s_hi - (kRegion - 1), 0);
+    col0 = s_lo & ~3;
+    ncols = s_hi >= 0 ? ((s_hi - col0 + 1 + 3) & ~3) : 0;
+    dst_off = 0;
+  }
+  const bool has_band = ncols > 0;               // a beta region entirely past the lattice stays dead
+  const uint32_t chunk_bytes = (uint32_t)ncols * W * 4u;
+
+  for (int k = tid; k < kBndStages * CH; k += blockDim.x) (&xs[0][0])[k] = kDead;
+  if (tid == 0) {
+    for (int r = 0; r < kBndStages; ++r) mbar_init(&full[r], 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    hoff[0] = 0.0;
+    hoff[1] = 0.0;
+    hmaxs[0] = f2ord(kDead);
+    hmaxs[1] = f2ord(kDead);
+  }
   // initial vector: alpha starts from the unit vector at state 0 (the virtual frame -1), betahat of the last
   // frame is 0 on the two final states (u = 0, 1).
   {
     const int idx = dir ? nb : 0;
-    if (!helper) {
+    if (consumer) {
       float v0 = kDead;
       if (u == 0 || (dir == 1 && u == 1 && S > 1)) v0 = 0.0f;
-      buf[0][H + tid] = v0;
-      brow0[(size_t)idx * Sq + u] = v0;
-      if (tid < H) buf[0][tid] = kDead;
-      if (lane == 0) wmx[0][warp] = f2ord((g == 0 && warp == 0) ? 0.0f : kDead);
-    } else if (lane == 0) {
-      boff0[(size_t)idx * G + g] = 0.0;
-    }
-  }
-
-  // consumer: enqueue the band column of step `st` into ring slot st % kBndStages
-  auto enqueue = [&](int st) {
-    if (st < nb) {
-      const int b = dir ? (nb - 1 - st) : st;
-      const float* xb = xf0 + (size_t)b * W * Sq;
-      float* dst = &xs[st % kBndStages][0][tid];
-      const int col = dir ? (S - 1 - u) : u;     // alpha: source column u-d; beta: column of s = S-1-u
-#pragma unroll
-      for (int d = 0; d < W; ++d) {
-        const bool ok = (u - d >= 0) && (dir ? (col >= 0) : true);
-        if (ok) cp_async_f32(dst + d * kRegion, xb + (size_t)d * Sq + (dir ? col : (u - d)));
-        else dst[d * kRegion] = kDead;
+      if (h == 0) {
+        buf[0][H + i] = v0;
+        brow0[(size_t)idx * Sq + u] = v0;
       }
+      if (tid < H) {
+        buf[0][tid] = kDead;
+        buf[1][tid] = kDead;
+      }
+      if (tid < 2) buf[tid][H + kRegion] = kDead;
+      if (lane == 0) wmx[0][warp] = f2ord((g == 0 && warp == 0) ? 0.0f : kDead);
+      if (tid == 0) boff0[(size_t)idx * G + g] = 0.0;
     }
-    cp_async_commit();
-  };
-  if (!helper) {
-#pragma unroll
-    for (int st = 0; st < kBndStages - 1; ++st) enqueue(st);
   }
   __syncthreads();
 
-  double off = 0.0;                              // helper: offset of the own region of the newest vector
-  bool halo_prev_alive = false;
-  for (int st = 0; st < nb; ++st) {
-    const float* prev = buf[st & 1];
-    float* cur = buf[(st + 1) & 1];
-    const int idx_out = dir ? (nb - 1 - st) : (st + 1);
-    // centring constant: the maximum of the own region of the previous vector (0 while the region is dead)
-    float mprev = ord2f(max(max(wmx[st & 1][0], wmx[st & 1][1]), max(wmx[st & 1][2], wmx[st & 1][3])));
-    const bool alive_prev = mprev > -1.0e29f;
-    const float c = alive_prev ? mprev : 0.0f;
-    if (!helper) {
-      enqueue(st + kBndStages - 1);
-      cp_async_wait<kBndStages - 1>();
-      const float* xc = &xs[st % kBndStages][0][tid];
-      float term[W];
-      float mx = kDead;
-#pragma unroll
-      for (int d = 0; d < W; ++d) {
-        term[d] = xc[d * kRegion] + prev[H + tid - d];
-        mx = fmaxf(mx, term[d]);
+  if (tma_warp) {
+    // ---------------------------------------------------------------------------------- band prefetch
+    auto issue = [&](int st) {
+      if (st < nb && has_band && lane == 0) {
+        const int b = dir ? (nb - 1 - st) : st;
+        const int slot = st % kBndStages;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of the slot
+        mbar_arrive_expect_tx(&full[slot], chunk_bytes);
+        tma_row_g2s(&xs[slot][dst_off], xf0 + ((size_t)b * Sq + col0) * W, chunk_bytes, &full[slot]);
       }
-      float sum = 0.0f;
-#pragma unroll
-      for (int d = 0; d < W; ++d) sum += fast_ex2(term[d] - mx);
-      const float val = (mx + fast_lg2(sum)) - c;
-      cur[H + tid] = val;
-      brow0[(size_t)idx_out * Sq + u] = val;
-      const int wm = __reduce_max_sync(0xffffffffu, f2ord(val));
-      if (lane == 0) wmx[(st + 1) & 1][warp] = wm;
-      if (tid >= kRegion - H && g + 1 < G)
-        st_tagged(halo0 + ((size_t)idx_out * G + g) * kHaloWords + (tid - (kRegion - H)),
-                  make_int2(__float_as_int(val), st + 1));
-    } else {
-      // helper warp: take the halo of the region below for the vector being produced, decide this region's offset
-      float hv = kDead;
-      double noff = 0.0;
-      bool halo_alive = false;
+    };
+    for (int st = 0; st < kBndStages - 1; ++st) issue(st);
+    if (has_band) mbar_wait(&full[0], 0u);
+    __syncthreads();                             // "start"
+    for (int st = 0; st < nb; ++st) {
+      issue(st + kBndStages - 1);                // its slot was consumed in step st-1
+      if (st + 1 < nb && has_band) mbar_wait(&full[(st + 1) % kBndStages], (uint32_t)((st + 1) / kBndStages) & 1u);
+      __syncthreads();                           // end of step st
+    }
+    return;
+  }
+  if (halo_warp) {
+    // ------------------------------------------------------------------------------ hand-over from region g-1
+    // Fetches the 2K values, the frame and the maximum of the halo of V_{st+1} while the consumers work on step st.
+    const int64_t pstep = (dir ? -1 : 1) * (int64_t)G * kHaloWords;
+    const int2* hp = halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + (g > 0 ? g - 1 : 0)) * kHaloWords + lane;
+    const bool polls = g > 0 && lane < kHaloWords;
+    int2 wpre = make_int2(0, 0);
+    if (polls) wpre = ld_tagged(hp);
+    __syncthreads();                             // "start"
+    for (int st = 0; st < nb; ++st) {
       if (g > 0) {
-        const int2* hp = halo0 + ((size_t)idx_out * G + (g - 1)) * kHaloWords;
-        int2 w = make_int2(0, 0);
-        if (lane < kHaloWords) {
-          do { w = ld_tagged(hp + lane); } while (w.y != st + 1);
+        // the words of this step were requested a step ago (the region below runs ahead): no L2 round trip here
+        int2 w = wpre;
+        if (polls) {
+          if (st + 1 < nb) wpre = ld_tagged(hp + pstep);
+          while (w.y != st + 1) w = ld_tagged(hp);
         }
         const int lo = __shfl_sync(0xffffffffu, w.x, H), hi = __shfl_sync(0xffffffffu, w.x, H + 1);
-        noff = __hiloint2double(hi, lo);
-        hv = (lane < H) ? __int_as_float(w.x) : kDead;
-        halo_alive = __ballot_sync(0xffffffffu, hv > -1.0e29f) != 0u;
+        const float hv = (lane < H) ? __int_as_float(w.x) : kDead;
+        if (lane < H) buf[(st + 1) & 1][lane] = hv;
+        const int hm = __reduce_max_sync(0xffffffffu, f2ord(hv));
+        if (lane == 0) {
+          hoff[(st + 1) & 1] = __hiloint2double(hi, lo);
+          hmaxs[(st + 1) & 1] = hm;
+        }
+        hp += pstep;
       }
-      // a region that stays dead this step adopts the offset of the region below, so the first values that
-      // flow in are taken over without rounding
-      const bool stays_dead = !alive_prev && !halo_prev_alive;
-      const double off_new = stays_dead ? (g > 0 ? noff : off) : off + (double)c;
-      if (lane < H) cur[lane] = (hv > -1.0e29f) ? hv + (float)(noff - off_new) : kDead;
-      if (lane == 0) {
-        boff0[(size_t)idx_out * G + g] = off_new;
-        off_s = off_new;
-      }
-      if (g + 1 < G && lane < 2) {
-        const int half = lane ? __double2hiint(off_new) : __double2loint(off_new);
-        st_tagged(halo0 + ((size_t)idx_out * G + g) * kHaloWords + H + lane, make_int2(half, st + 1));
-      }
-      off = off_new;
-      halo_prev_alive = halo_alive;
+      __syncthreads();                           // end of step st
     }
-    __syncthreads();
+    return;
+  }
+  if (frame_warp) {
+    // ------------------------------------------------------------------------------------ frames of reference
+    // Stored values of vector V_v are relative to the fp64 frame F(v) of this region.  F(st+2) is fixed here, in
+    // the shadow of step st, from what is known when the step starts: the maximum of the own part of V_st and of
+    // its halo, each extrapolated two steps by its drift.  Consumers never compute an offset: they read the own
+    // shift F(st)-F(st+1) and form the halo shift from F(st+1).  Any frame is correct; a good one keeps stored
+    // values near 0.  A region with nothing alive takes the lower region's frame, so the first values that flow
+    // in are shifted by one step's drift only.
+    const int64_t vstep = dir ? -1 : 1;
+    double* bo = boff0 + (size_t)(dir ? (nb - 1) : 1) * G + g;          // frame of V_1
+    int2* ho_words = halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + g) * kHaloWords + H + (lane & 1);
+    const bool pub = g + 1 < G && lane < 2;
+    double F1 = 0.0;                              // frame of V_{st+1}
+    double F0 = 0.0;                              // frame of V_st
+    double own_prev = 0.0, halo_prev = 0.0;
+    bool own_had = false, halo_had = false;
+    if (lane == 0) {
+      oshift[0] = 0.0f;
+      Fd[0] = 0.0;
+      *bo = 0.0;
+    }
+    if (pub) st_tagged(ho_words, make_int2(0, 1));
+    __syncthreads();                             // "start"
+    for (int st = 0; st < nb; ++st) {
+      const int* wm = wmx[st & 1];
+      const float m0 = ord2f(max(max(wm[0], wm[1]), max(wm[2], wm[3])));   // own maximum of V_st, frame F0
+      const double ho = hoff[st & 1];
+      const float hm = ord2f(hmaxs[st & 1]);                               // halo maximum of V_st, frame ho
+      const bool own_alive = m0 > -1.0e29f, halo_alive = hm > -1.0e29f;
+      const double tro = F0 + (double)m0, trh = ho + (double)hm;
+      const double co = own_had ? fma(2.0, tro - own_prev, tro) : tro;
+      const double ch = halo_had ? fma(2.0, trh - halo_prev, trh) : trh;
+      double F2 = (g > 0) ? ho : F1;
+      if (own_alive) F2 = co;
+      if (halo_alive) F2 = own_alive ? fmax(co, ch) : ch;
+      own_prev = tro; own_had = own_alive;
+      halo_prev = trh; halo_had = halo_alive;
+      if (st + 1 < nb) {
+        bo += vstep * G;
+        ho_words += vstep * G * kHaloWords;
+        if (lane == 0) {
+          oshift[(st + 1) & 1] = (float)(F1 - F2);
+          Fd[(st + 1) & 1] = F2;
+          *bo = F2;
+        }
+        if (pub) st_tagged(ho_words, make_int2(lane ? __double2hiint(F2) : __double2loint(F2), st + 2));
+      }
+      F0 = F1;
+      F1 = F2;
+      __syncthreads();                           // end of step st
+    }
+    return;
   }
 
+  // -------------------------------------------------------------------------------------- consumers
+  // Per-thread constants of the term loop: this thread owns terms d = h*(K+1) + k.  Smem addresses are
+  // precomputed for ring slot 0 / buffer 0; the step adds a compile-time offset.  Thread h=1 has one term less:
+  // its last slot points at a permanently dead cell.
+  const int srow = S - 1 - u;                     // beta: band row of this destination
+  const bool forced_dead = (dir == 1 && srow < 0);
+  const float* xp[kTermsPerThread];
+  const float* pp[kTermsPerThread];
+  float hmask[kTermsPerThread];                   // 1 where the term's source lies in the halo
+#pragma unroll
+  for (int k = 0; k < kTermsPerThread; ++k) {
+    const int d = h * kTermsPerThread + k;
+    const bool valid = d <= W - 1;
+    const int dd = valid ? d : 0;
+    const int xo = dir ? ((forced_dead ? 0 : srow - col0) * W + dd) : ((i + H - dd) * W + dd);
+    const int po = valid ? (H + i - dd) : (H + kRegion);
+    xp[k] = &xs[0][xo];
+    pp[k] = &buf[0][po];
+    hmask[k] = (valid && po < H) ? 1.0f : 0.0f;
+  }
+  const bool uses_halo = warp == 0;              // destinations 0..15 of the region reach below it
+  const int64_t vstep = dir ? -1 : 1;            // boundary vector index advance per step
+  float* bout = brow0 + (size_t)(dir ? (nb - 1) : 1) * Sq + u;
+  int2* hout = halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + g) * kHaloWords + (i - (kRegion - H));
+  const bool pub_val = h == 0 && i >= kRegion - H && g + 1 < G;
+  constexpr int BS = H + kRegion + 1;            // buffer stride
+  __syncthreads();                               // "start"
+  // one step: V_st (buffer PAR) -> V_{st+1} (buffer PAR^1), band chunk in ring slot SLOT
+#define DAE_BND_STEP(SLOT, PAR)                                                                            \
+  {                                                                                                        \
+    const float osh = oshift[PAR];                                                                         \
+    float term[kTermsPerThread];                                                                           \
+    if (uses_halo) {                                                                                       \
+      const float dsh = (float)(hoff[PAR] - Fd[PAR]) - osh;                                                \
+      _Pragma("unroll") for (int k = 0; k < kTermsPerThread; ++k)                                          \
+        term[k] = (xp[k][(SLOT) * CH] + pp[k][(PAR) * BS]) + fmaf(hmask[k], dsh, osh);                     \
+    } else {                                                                                               \
+      _Pragma("unroll") for (int k = 0; k < kTermsPerThread; ++k)                                          \
+        term[k] = xp[k][(SLOT) * CH] + pp[k][(PAR) * BS];                                                  \
+    }                                                                                                      \
+    float mx = fmaxf(fmaxf(term[0], term[1]), term[2]);                                                    \
+    _Pragma("unroll") for (int k = 3; k < kTermsPerThread; ++k) mx = fmaxf(mx, term[k]);                   \
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));                                                   \
+    float s0 = 0.0f, s1 = 0.0f;                                                                            \
+    _Pragma("unroll") for (int k = 0; k < kTermsPerThread; ++k) {                                          \
+      const float e = fast_ex2(term[k] - mx);                                                              \
+      if (k & 1) s1 += e; else s0 += e;                                                                    \
+    }                                                                                                      \
+    float sum = s0 + s1;                                                                                   \
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);                                                           \
+    float val = mx + fast_lg2(sum);                                                                        \
+    if (!uses_halo) val += osh;                                                                            \
+    if (forced_dead) val = kDead;                                                                          \
+    if (h == 0) {                                                                                          \
+      buf[(PAR) ^ 1][H + i] = val;                                                                         \
+      *bout = val;                                                                                         \
+    }                                                                                                      \
+    if (pub_val) st_tagged(hout, make_int2(__float_as_int(val), st + 1));                                  \
+    const int wmv = __reduce_max_sync(0xffffffffu, f2ord(val));                                            \
+    if (lane == 0) wmx[(PAR) ^ 1][warp] = wmv;                                                             \
+    bout += vstep * Sq;                                                                                    \
+    hout += vstep * G * kHaloWords;                                                                        \
+    ++st;                                                                                                  \
+    __syncthreads();                                                                                       \
+  }
+  int st = 0;
+  for (; st + 3 < nb;) {
+    DAE_BND_STEP(0, 0)
+    DAE_BND_STEP(1, 1)
+    DAE_BND_STEP(2, 0)
+    DAE_BND_STEP(3, 1)
+  }
+  if (st < nb) DAE_BND_STEP(0, 0)
+  if (st < nb) DAE_BND_STEP(1, 1)
+  if (st < nb) DAE_BND_STEP(2, 0)
+#undef DAE_BND_STEP
+
   // log-likelihood from the final vector: alpha ends on the last two states, betahat(-1) starts on state 0 (u = S-1)
-  if (!helper && u == S - 1) {
+  if (h == 0 && u == S - 1) {
     const float* fin = buf[nb & 1];
-    const float e1 = fin[H + tid];
-    const float e2 = (dir == 0 && S > 1) ? fin[H + tid - 1] : kDead;
-    const float tail = lse2_n(e1, e2);
-    const double ll2 = (tail < -1.0e29f) ? -(double)CUDART_INF_F : off_s + (double)tail;
+    const float e1 = fin[H + i];
+    const bool in_halo = i == 0;                   // state S-2 belongs to the region below
+    const float e2 = (dir == 0 && S > 1) ? fin[H + i - 1] : kDead;
+    // the region offset lives in warp 0; everyone can re-read it from the boundary array
+    const int idx_fin = dir ? 0 : nb;
+    const double off_fin = boff0[(size_t)idx_fin * G + g];
+    const float e2s = in_halo ? e2 + (float)(hoff[nb & 1] - off_fin) : e2;
+    const float tail = lse2_n(e1, e2s);
+    const double ll2 = (tail < -1.0e29f) ? -(double)CUDART_INF_F : off_fin + (double)tail;
     sc.ll2[dir * N + n] = ll2;
     if (dir == 0) nll[n] = (float)(-ll2 * kLn2d);
   }
@@ -485,7 +637,7 @@ int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, i
   ctc_xfer_kernel<kBlkK><<<dim3(sc.nblk, tiles, N), kXferTile, 0, st>>>(lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len,
                                                                        tgt_len, blank, sc);
   DAE_LAUNCH_OK();
-  ctc_boundary_kernel<kBlkK><<<dim3(sc.G, 2, N), kRegion + 32, 0, st>>>(T, Lmax, in_len, tgt_len, nll, sc);
+  ctc_boundary_kernel<kBlkK><<<dim3(sc.G, 2, N), kBndThreads, 0, st>>>(T, Lmax, in_len, tgt_len, nll, sc);
   DAE_LAUNCH_OK();
   int P, NTc;
   lat_geometry(Lmax, P, NTc);

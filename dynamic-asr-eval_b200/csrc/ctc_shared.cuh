@@ -21,7 +21,7 @@ struct CtcScratch {           // carved out of the caller's scratch buffer
   double* ll2;                // [4][N]   log2-likelihood from the alpha CTA, the beta CTA, then debug totals
   int Sp, Lp;
   // ---- time-blocked path only (ctc_blocked.cu); null / 0 when the shape is not eligible
-  float* xfer;                // [N][nblk][2K+1][Sq]  K-frame transfer bands, log2 units: xfer[b][d][s] = paths s -> s+d
+  float* xfer;                // [N][nblk][Sq][2K+1]  K-frame transfer bands, log2 units: xfer[b][s][d] = paths s -> s+d
   float* bound;               // [2][N][nblk+1][Sq]   lattice vectors at block boundaries, centred per 128-state region
   double* boff;               // [2][N][nblk+1][G]    offset of each 128-state region of a boundary vector
   int2* halo;                 // [2][N][nblk+1][G][kHaloWords]  tagged {bits, tag} words handed to the next region
@@ -30,7 +30,7 @@ struct CtcScratch {           // carved out of the caller's scratch buffer
 
 constexpr int kBlkK = 8;                          // frames per time block
 constexpr int kBlkW = 2 * kBlkK + 1;              // a state moves at most two places per frame
-constexpr int kRegion = 128;                      // states per boundary-scan CTA
+constexpr int kRegion = 64;                       // states per boundary-scan CTA
 constexpr int kHaloWords = 2 * kBlkK + 2;         // 2K values + the region offset as two 32-bit halves
 constexpr int kBlkMaxN = 8;                       // batches larger than this fill the GPU with the per-frame chain
 constexpr size_t kBlkMaxXferBytes = (size_t)256 << 20;
@@ -135,6 +135,37 @@ __device__ __forceinline__ float lse3_n(float a, float b, float c) {
   const float lo = fminf(a, b), hi = fmaxf(a, b);
   const float m = fmaxf(hi, c), mid = fminf(hi, c);
   return m + fast_lg2(1.0f + fast_ex2(mid - m) + fast_ex2(lo - m));
+}
+
+// ---- mbarrier / bulk-copy (TMA) helpers -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion is counted on `bar`.
+__device__ __forceinline__ void tma_row_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// Fallback for rows that are not 16-byte aligned: per-thread 4-byte cp.async, tracked by the same mbarrier.
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // ctc_blocked.cu: fills the same scratch (alpha, beta_rev, offsets, label groups, ll2) and nll as ctc_lattice_kernel.

@@ -157,12 +157,11 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
                     float* __restrict__ nll, CtcScratch sc) {
   constexpr int W = 2 * K + 1, H = 2 * K, CH = (kRegion + H) * W;
   __shared__ __align__(128) float xs[kBndStages][CH];   // band rows of the states this region reads, per step
-  __shared__ float buf[2][H + kRegion + 1];             // [halo of the region below (raw) | own region | dead cell]
+  __shared__ __align__(8) float buf[2][H + kRegion + 2];   // [halo of the region below (raw) | own region | dead cell, pad]
   __shared__ double hoff[2];                            // offset the halo values of each buffer are relative to
   __shared__ int hmaxs[2];                              // their maximum (order-preserving int)
   __shared__ float oshift[2];                           // per step: shift of own values into the new frame
   __shared__ double Fd[2];                              // per step: the new frame itself
-  __shared__ int wmx[2][2 * kRegion / 32];              // per-warp maxima of the own region of each buffer
   __shared__ uint64_t full[kBndStages];
   const int g = blockIdx.x, dir = blockIdx.y, n = blockIdx.z, N = gridDim.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -234,7 +233,6 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
         buf[1][tid] = kDead;
       }
       if (tid < 2) buf[tid][H + kRegion] = kDead;
-      if (lane == 0) wmx[0][warp] = f2ord((g == 0 && warp == 0) ? 0.0f : kDead);
       if (tid == 0) boff0[(size_t)idx * G + g] = 0.0;
     }
   }
@@ -267,15 +265,20 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
     const int64_t pstep = (dir ? -1 : 1) * (int64_t)G * kHaloWords;
     const int2* hp = halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + (g > 0 ? g - 1 : 0)) * kHaloWords + lane;
     const bool polls = g > 0 && lane < kHaloWords;
-    int2 wpre = make_int2(0, 0);
-    if (polls) wpre = ld_tagged(hp);
+    // Words are requested two steps before they are consumed (one L2 round trip is longer than a step); the
+    // region below runs ahead by that much once the pipeline has filled.
+    int2 wa = make_int2(0, 0), wb = make_int2(0, 0);       // requests for the current and the next step
+    if (polls) {
+      wa = ld_tagged(hp);
+      if (nb > 1) wb = ld_tagged(hp + pstep);
+    }
     __syncthreads();                             // "start"
     for (int st = 0; st < nb; ++st) {
       if (g > 0) {
-        // the words of this step were requested a step ago (the region below runs ahead): no L2 round trip here
-        int2 w = wpre;
+        int2 w = wa;
+        wa = wb;
         if (polls) {
-          if (st + 1 < nb) wpre = ld_tagged(hp + pstep);
+          if (st + 2 < nb) wb = ld_tagged(hp + 2 * pstep);
           while (w.y != st + 1) w = ld_tagged(hp);
         }
         const int lo = __shfl_sync(0xffffffffu, w.x, H), hi = __shfl_sync(0xffffffffu, w.x, H + 1);
@@ -304,9 +307,12 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
     double* bo = boff0 + (size_t)(dir ? (nb - 1) : 1) * G + g;          // frame of V_1
     int2* ho_words = halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + g) * kHaloWords + H + (lane & 1);
     const bool pub = g + 1 < G && lane < 2;
+    // Frames are fp64 sums of fp32 steps; all decisions are made on small fp32 quantities relative to the
+    // newest frame F1 = F(st+1), so the per-step chain is a dozen fp32 instructions and two fp64 adds.
     double F1 = 0.0;                              // frame of V_{st+1}
-    double F0 = 0.0;                              // frame of V_st
-    double own_prev = 0.0, halo_prev = 0.0;
+    float s01 = 0.0f;                             // F(st) - F(st+1)
+    float s10 = 0.0f;                             // F(st-1) - F(st)
+    float m0p = 0.0f, hmp = 0.0f, hrelp = 0.0f;   // previous own max / halo max / halo frame relative to F(st)
     bool own_had = false, halo_had = false;
     if (lane == 0) {
       oshift[0] = 0.0f;
@@ -316,30 +322,41 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
     if (pub) st_tagged(ho_words, make_int2(0, 1));
     __syncthreads();                             // "start"
     for (int st = 0; st < nb; ++st) {
-      const int* wm = wmx[st & 1];
-      const float m0 = ord2f(max(max(wm[0], wm[1]), max(wm[2], wm[3])));   // own maximum of V_st, frame F0
-      const double ho = hoff[st & 1];
-      const float hm = ord2f(hmaxs[st & 1]);                               // halo maximum of V_st, frame ho
+      // own maximum of V_st (relative to F(st)), straight from the vector the consumers left in smem
+      const float2 pv = *reinterpret_cast<const float2*>(&buf[st & 1][H + 2 * lane]);
+      float m0 = fmaxf(pv.x, pv.y);
+#pragma unroll
+      for (int q = 1; q < kRegion / 64; ++q) {
+        const float2 pq = *reinterpret_cast<const float2*>(&buf[st & 1][H + 64 * q + 2 * lane]);
+        m0 = fmaxf(m0, fmaxf(pq.x, pq.y));
+      }
+      m0 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(m0)));
+      const float hm = ord2f(hmaxs[st & 1]);      // halo maximum of V_st, relative to the lower region's frame
+      const float hrel = (float)(hoff[st & 1] - F1);
       const bool own_alive = m0 > -1.0e29f, halo_alive = hm > -1.0e29f;
-      const double tro = F0 + (double)m0, trh = ho + (double)hm;
-      const double co = own_had ? fma(2.0, tro - own_prev, tro) : tro;
-      const double ch = halo_had ? fma(2.0, trh - halo_prev, trh) : trh;
-      double F2 = (g > 0) ? ho : F1;
-      if (own_alive) F2 = co;
-      if (halo_alive) F2 = own_alive ? fmax(co, ch) : ch;
-      own_prev = tro; own_had = own_alive;
-      halo_prev = trh; halo_had = halo_alive;
+      // true maxima relative to F1, extrapolated two steps by their drift
+      const float ao = m0 + s01;
+      const float co = own_had ? fmaf(2.0f, (m0 - m0p) - s10, ao) : ao;
+      const float ah = hm + hrel;
+      const float ch = halo_had ? fmaf(2.0f, ah - (hmp + hrelp), ah) : ah;
+      float delta = (g > 0) ? hrel : 0.0f;        // nothing alive: take the lower region's frame
+      if (own_alive) delta = co;
+      if (halo_alive) delta = own_alive ? fmaxf(co, ch) : ch;
+      const double F2 = F1 + (double)delta;
+      m0p = m0; own_had = own_alive;
+      hmp = hm; hrelp = hrel - delta; halo_had = halo_alive;     // relative to F2, the next step's F1
       if (st + 1 < nb) {
         bo += vstep * G;
         ho_words += vstep * G * kHaloWords;
         if (lane == 0) {
-          oshift[(st + 1) & 1] = (float)(F1 - F2);
+          oshift[(st + 1) & 1] = -delta;
           Fd[(st + 1) & 1] = F2;
           *bo = F2;
         }
         if (pub) st_tagged(ho_words, make_int2(lane ? __double2hiint(F2) : __double2loint(F2), st + 2));
       }
-      F0 = F1;
+      s10 = s01;
+      s01 = -delta;
       F1 = F2;
       __syncthreads();                           // end of step st
     }
@@ -371,7 +388,7 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
   float* bout = brow0 + (size_t)(dir ? (nb - 1) : 1) * Sq + u;
   int2* hout = halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + g) * kHaloWords + (i - (kRegion - H));
   const bool pub_val = h == 0 && i >= kRegion - H && g + 1 < G;
-  constexpr int BS = H + kRegion + 1;            // buffer stride
+  constexpr int BS = H + kRegion + 2;            // buffer stride
   __syncthreads();                               // "start"
   // one step: V_st (buffer PAR) -> V_{st+1} (buffer PAR^1), band chunk in ring slot SLOT
 #define DAE_BND_STEP(SLOT, PAR)                                                                            \
@@ -404,8 +421,6 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
       *bout = val;                                                                                         \
     }                                                                                                      \
     if (pub_val) st_tagged(hout, make_int2(__float_as_int(val), st + 1));                                  \
-    const int wmv = __reduce_max_sync(0xffffffffu, f2ord(val));                                            \
-    if (lane == 0) wmx[(PAR) ^ 1][warp] = wmv;                                                             \
     bout += vstep * Sq;                                                                                    \
     hout += vstep * G * kHaloWords;                                                                        \
     ++st;                                                                                                  \
@@ -455,8 +470,8 @@ __host__ __device__ inline FillSmem fill_smem_layout(int Lp, int Sp) {
 
 // grid (nblk, 2, N): K ordinary lattice steps of block b in direction dir, starting from the boundary vector
 // the scan left (alpha: the vector before the block; beta: betahat of the block's last frame).
-template <int P, int K>
-__global__ void __launch_bounds__(kLatThreads - 64)
+template <int P, int K, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 ctc_fill_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, const int64_t* __restrict__ tgt,
                 int64_t tgt_stride, int Lmax, const int64_t* __restrict__ in_len,
                 const int64_t* __restrict__ tgt_len, int blank, CtcScratch sc, FillSmem lay) {
@@ -613,16 +628,17 @@ ctc_fill_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, con
   }
 }
 
-template <int P>
+template <int P, int MAXT, int MINB>
 static int launch_fill(int NTc, cudaStream_t st, int N, const float* lp, int64_t sT, int64_t sN, int T,
                        const int64_t* tgt, int64_t tgt_stride, int Lmax, const int64_t* in_len,
                        const int64_t* tgt_len, int blank, const CtcScratch& sc) {
   const FillSmem lay = fill_smem_layout(sc.Lp, sc.Sp);
   if (lay.total > 200 * 1024) return DAE_E_TOOBIG;
+  auto kern = ctc_fill_kernel<P, kBlkK, MAXT, MINB>;
   if (lay.total > 48 * 1024)
-    DAE_CUDA(cudaFuncSetAttribute(ctc_fill_kernel<P, kBlkK>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
-  ctc_fill_kernel<P, kBlkK><<<dim3(sc.nblk, 2, N), NTc, lay.total, st>>>(lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len,
-                                                                        tgt_len, blank, sc, lay);
+    DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+  kern<<<dim3(sc.nblk, 2, N), NTc, lay.total, st>>>(lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, sc,
+                                                    lay);
   DAE_LAUNCH_OK();
   return 0;
 }
@@ -641,9 +657,15 @@ int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, i
   DAE_LAUNCH_OK();
   int P, NTc;
   lat_geometry(Lmax, P, NTc);
-  if (P <= 1) return launch_fill<1>(NTc, st, N, lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, sc);
-  if (P <= 2) return launch_fill<2>(NTc, st, N, lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, sc);
-  return launch_fill<4>(NTc, st, N, lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, sc);
+#define DAE_FILL(PP, MT, MB) \
+  return launch_fill<PP, MT, MB>(NTc, st, N, lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, sc)
+  constexpr int kMaxC = kLatThreads - 64;
+  if (P <= 1 && NTc <= 320) DAE_FILL(1, 320, 4);       // short label sequences: several blocks per SM
+  if (P <= 1 && NTc <= 640) DAE_FILL(1, 640, 2);
+  if (P <= 1) DAE_FILL(1, kMaxC, 1);
+  if (P <= 2) DAE_FILL(2, kMaxC, 1);
+  DAE_FILL(4, kMaxC, 1);
+#undef DAE_FILL
 }
 
 }  // namespace dae

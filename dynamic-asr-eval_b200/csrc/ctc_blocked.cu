@@ -496,17 +496,25 @@ ctc_fill_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, con
     a1[tid - 4] = kDead;
   }
   __syncthreads();
-  if (dir == 0 && b == 0) {                      // label grouping for the gradient pass
-    for (int k = tid; k < L; k += NTc) {
+  if (dir == 0) {
+    // Label grouping for the gradient pass (first occurrence + next occurrence of each class), spread over the
+    // alpha CTAs of the sample: this CTA takes label positions [k0, k1), one per warp, lanes scan the sequence.
+    const int per = (L + nb - 1) / nb;
+    const int k0 = b * per, k1 = min(L, k0 + per);
+    for (int k = k0 + warp; k < k1; k += nw) {
       const int c = lab[k];
-      int nxt = -1;
-      for (int j = k + 1; j < L; ++j)
-        if (lab[j] == c) { nxt = j; break; }
-      int first = 1;
-      for (int j = k - 1; j >= 0; --j)
-        if (lab[j] == c) { first = 0; break; }
-      sc.next_same[(int64_t)n * sc.Lp + k] = nxt;
-      sc.leader[(int64_t)n * sc.Lp + k] = first;
+      int nxt = 0x7fffffff, before = 0;
+      for (int j = lane; j < L; j += 32) {
+        const bool same = lab[j] == c;
+        if (same && j > k) nxt = min(nxt, j);
+        if (same && j < k) before = 1;
+      }
+      nxt = __reduce_min_sync(0xffffffffu, nxt);
+      before = __reduce_max_sync(0xffffffffu, before);
+      if (lane == 0) {
+        sc.next_same[(int64_t)n * sc.Lp + k] = (nxt == 0x7fffffff) ? -1 : nxt;
+        sc.leader[(int64_t)n * sc.Lp + k] = before ? 0 : 1;
+      }
     }
   }
   int p2[P];

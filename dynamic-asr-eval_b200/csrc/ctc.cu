@@ -467,6 +467,12 @@ extern "C" int dae_ctc_grad(const float* lp, int64_t sT, int64_t sN, int T, int 
   if (N == 0 || T == 0) return 0;
   CtcScratch sc;
   ctc_carve(sc, const_cast<void*>(scratch), T, N, Lmax);
+  const int vec_g = aligned16(lp) && aligned16(grad) && (C % 4 == 0) && (sT % 4 == 0) && (sN % 4 == 0);
+  if (sc.xfer) {                                         // blocked path: alpha/beta rows are rebuilt per block
+    rc = ctc_blocked_grad(lp, sT, sN, T, N, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, gout, gout_stride, grad,
+                          sc, vec_g, (cudaStream_t)stream);
+    if (rc != 1) return rc;
+  }
   const size_t smem = (size_t)((C + 3) & ~3) * 4 + (size_t)sc.Lp * 4;
   if (smem > 200 * 1024) return DAE_E_TOOBIG;
   if (smem > 48 * 1024)

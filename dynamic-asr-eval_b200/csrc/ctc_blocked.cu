@@ -136,6 +136,28 @@ ctc_xfer_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, con
   float4* dst = reinterpret_cast<float4*>(sc.xfer + ((size_t)(n * sc.nblk + b) * sc.Sq + s0) * W);
   const float4* src = reinterpret_cast<const float4*>(outs);
   for (int i = tid; i < ncols * W / 4; i += kXferTile) dst[i] = src[i];
+  if (blockIdx.y == 0) {
+    // Label grouping for the gradient pass (first occurrence + next occurrence of each class), spread over the
+    // sample's time blocks: this CTA takes label positions [k0, k1), one per warp, lanes scan the sequence.
+    const int lane = tid & 31, warp = tid >> 5;
+    const int per = (L + nb - 1) / nb;
+    const int k0 = b * per, k1 = min(L, k0 + per);
+    for (int k = k0 + warp; k < k1; k += kXferTile / 32) {
+      const int c = (int)trow[k];
+      int nxt = 0x7fffffff, before = 0;
+      for (int j = lane; j < L; j += 32) {
+        const bool same = (int)trow[j] == c;
+        if (same && j > k) nxt = min(nxt, j);
+        if (same && j < k) before = 1;
+      }
+      nxt = __reduce_min_sync(0xffffffffu, nxt);
+      before = __reduce_max_sync(0xffffffffu, before);
+      if (lane == 0) {
+        sc.next_same[(int64_t)n * sc.Lp + k] = (nxt == 0x7fffffff) ? -1 : nxt;
+        sc.leader[(int64_t)n * sc.Lp + k] = before ? 0 : 1;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ 2. boundary scan
@@ -496,27 +518,6 @@ ctc_fill_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, con
     a1[tid - 4] = kDead;
   }
   __syncthreads();
-  if (dir == 0) {
-    // Label grouping for the gradient pass (first occurrence + next occurrence of each class), spread over the
-    // alpha CTAs of the sample: this CTA takes label positions [k0, k1), one per warp, lanes scan the sequence.
-    const int per = (L + nb - 1) / nb;
-    const int k0 = b * per, k1 = min(L, k0 + per);
-    for (int k = k0 + warp; k < k1; k += nw) {
-      const int c = lab[k];
-      int nxt = 0x7fffffff, before = 0;
-      for (int j = lane; j < L; j += 32) {
-        const bool same = lab[j] == c;
-        if (same && j > k) nxt = min(nxt, j);
-        if (same && j < k) before = 1;
-      }
-      nxt = __reduce_min_sync(0xffffffffu, nxt);
-      before = __reduce_max_sync(0xffffffffu, before);
-      if (lane == 0) {
-        sc.next_same[(int64_t)n * sc.Lp + k] = (nxt == 0x7fffffff) ? -1 : nxt;
-        sc.leader[(int64_t)n * sc.Lp + k] = before ? 0 : 1;
-      }
-    }
-  }
   int p2[P];
   bool skip[P];
   float xl[P][K], xb[K];
@@ -651,6 +652,382 @@ static int launch_fill(int NTc, cudaStream_t st, int N, const float* lp, int64_t
   return 0;
 }
 
+// Rows of alpha / beta for every frame, from the boundary vectors (only needed when the fused gradient kernel does
+// not fit: ctc_grad_kernel reads them from the scratch).
+int ctc_blocked_fill(const float* lp, int64_t sT, int64_t sN, int T, int N, const int64_t* tgt, int64_t tgt_stride,
+                     int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank, const CtcScratch& sc,
+                     cudaStream_t st) {
+  int P, NTc;
+  lat_geometry(Lmax, P, NTc);
+#define DAE_FILL(PP, MT, MB) \
+  return launch_fill<PP, MT, MB>(NTc, st, N, lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, sc)
+  constexpr int kMaxC = kLatThreads - 64;
+  if (P <= 1 && NTc <= 320) DAE_FILL(1, 320, 4);       // short label sequences: several blocks per SM
+  if (P <= 1 && NTc <= 640) DAE_FILL(1, 640, 2);
+  if (P <= 1) DAE_FILL(1, kMaxC, 1);
+  if (P <= 2) DAE_FILL(2, kMaxC, 1);
+  DAE_FILL(4, kMaxC, 1);
+#undef DAE_FILL
+}
+
+// ------------------------------------------------------------------------------------------ 4. fused block fill + gradient
+struct BgSmem { int red, wmx, offs, bsum, xbs, lab, nxt, rowsA, rowsB, gam, row_stride, total; };
+__host__ __device__ inline BgSmem bg_smem_layout(int Lp, int Sp, int K) {
+  BgSmem m;
+  m.red = 0;                                             // double[2][32]
+  m.offs = m.red + 2 * 32 * 8;                           // double[2][K]
+  m.wmx = m.offs + 2 * K * 8;                            // int[2 dirs][2 slots][32]
+  m.bsum = m.wmx + 4 * 32 * 4;                           // float[32][K]: per-warp blank occupancy sums
+  m.xbs = m.bsum + 32 * K * 4;                           // float[K]: blank emission (log2) per frame
+  m.lab = m.xbs + K * 4;
+  m.nxt = m.lab + Lp * 4;                                // int[Lp]: next label position with the same class
+  m.row_stride = Sp + 4;                                 // floats; 4 dead cells in front of every row
+  m.rowsA = (int)align_up((size_t)m.nxt + (size_t)Lp * 4, 16);
+  m.rowsB = m.rowsA + K * m.row_stride * 4;
+  m.gam = m.rowsB + K * m.row_stride * 4;                // float[K][Lp]: label emissions, then label occupancies
+  m.total = m.gam + K * Lp * 4;
+  return m;
+}
+
+// grid (nblk, N): everything the gradient of block b needs, without a round trip through HBM.
+//   0. dense part of the block's K gradient rows, g*exp(lp), streamed straight from lp to grad;
+//   1. the K alpha rows and K beta rows of the block, rebuilt in shared memory from the scan's boundary vectors.
+//      The two recurrences are independent, so every thread advances its alpha pair(s) and its beta pair(s) in the
+//      same step: twice the work per barrier on a latency-bound chain;
+//   2. occupancies 2^(alpha~ + beta~ + (offA + offB - ll2) - x) of every state of every row; per class sums by
+//      walking the first-occurrence lists (deterministic order), then the few classes that occur in the label
+//      sequence (and blank) are overwritten with g*(exp(lp) - occupancy).
+template <int P, int K, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, int C,
+                      const int64_t* __restrict__ tgt, int64_t tgt_stride, int Lmax,
+                      const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len, int blank,
+                      const float* __restrict__ gout, int64_t gout_stride, float* __restrict__ grad, CtcScratch sc,
+                      BgSmem lay, int vec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x, n = blockIdx.y, N = gridDim.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NTc = blockDim.x, nw = NTc >> 5;
+  int Tn, L;
+  clamp_lengths(in_len, tgt_len, n, T, Lmax, Tn, L);
+  const int S = 2 * L + 1;
+  const int t0 = b * K;
+  const int kb = max(0, min(K, Tn - t0));        // frames of this block inside the sample
+  const int krows = max(0, min(K, T - t0));      // gradient rows this CTA owns
+
+  double* red = reinterpret_cast<double*>(smem_raw + lay.red);
+  double* offs = reinterpret_cast<double*>(smem_raw + lay.offs);      // [0..K): alpha rows, [K..2K): beta rows
+  int* wmx = reinterpret_cast<int*>(smem_raw + lay.wmx);
+  float* bsum_s = reinterpret_cast<float*>(smem_raw + lay.bsum);
+  float* xbs = reinterpret_cast<float*>(smem_raw + lay.xbs);
+  int* lab = reinterpret_cast<int*>(smem_raw + lay.lab);
+  int* nxt = reinterpret_cast<int*>(smem_raw + lay.nxt);
+  float* rowsA = reinterpret_cast<float*>(smem_raw + lay.rowsA) + 4;
+  float* rowsB = reinterpret_cast<float*>(smem_raw + lay.rowsB) + 4;
+  float* gam = reinterpret_cast<float*>(smem_raw + lay.gam);
+  const int RS = lay.row_stride, Lp = sc.Lp;
+  const float* base = lp + n * sN;
+  const float g = gout[n * gout_stride];
+
+  // ---- 0. dense part (zeros for the padding frames of a short sample): all K rows of a column chunk are loaded
+  // before any is stored, so a thread keeps K independent 128-bit loads in flight.
+  auto dense = [&]() {
+    if (vec) {
+      for (int i = tid; i < (C >> 2); i += NTc) {
+        float4 v4[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (k < kb) v4[k] = __ldcs(reinterpret_cast<const float4*>(base + (int64_t)(t0 + k) * sT) + i);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (k < krows) {
+            float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < kb) o4 = make_float4(__expf(v4[k].x) * g, __expf(v4[k].y) * g, __expf(v4[k].z) * g, __expf(v4[k].w) * g);
+            __stcs(reinterpret_cast<float4*>(grad + ((int64_t)(t0 + k) * N + n) * C) + i, o4);
+          }
+        }
+      }
+    } else {
+      for (int k = 0; k < krows; ++k) {
+        float* orow = grad + ((int64_t)(t0 + k) * N + n) * C;
+        const float* xrow = base + (int64_t)(t0 + k) * sT;
+        for (int i = tid; i < C; i += NTc) orow[i] = (k < kb) ? __expf(xrow[i]) * g : 0.0f;
+      }
+    }
+  };
+  // half of the grid streams first and runs its chains later, the other half the other way round, so the two
+  // CTAs that share an SM overlap memory traffic with the latency-bound chains
+  const bool dense_first = (int)blockIdx.x * 2 < (int)gridDim.x || kb == 0;
+  if (dense_first) dense();
+  if (kb == 0) return;
+
+  // ---- 1a. labels, list links, emissions of the block's frames at every label state
+  const int t1 = t0 + kb - 1;
+  for (int k = tid; k < L; k += NTc) {
+    lab[k] = (int)tgt[n * tgt_stride + k];
+    nxt[k] = sc.next_same[(int64_t)n * Lp + k];
+  }
+  for (int r = tid; r < 4 * 2 * K; r += NTc) {
+    float* row = (r < 4 * K) ? rowsA + (r >> 2) * RS : rowsB + ((r >> 2) - K) * RS;
+    row[(r & 3) - 4] = kDead;
+  }
+  if (tid < K) xbs[tid] = (tid < kb) ? base[(int64_t)(t0 + tid) * sT + blank] * kLog2e : kDead;
+  int p2[P];
+  bool lead_q[P];
+  float xla[P][K];                               // emissions (log2) of this thread's label states, per frame
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int p = tid + j * NTc;
+    p2[j] = 2 * p;
+    lead_q[j] = (p < L) ? (sc.leader[(int64_t)n * Lp + p] != 0) : false;
+    const int cls = (p < L) ? (int)tgt[n * tgt_stride + p] : blank;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      xla[j][k] = (k < kb && p < L) ? base[(int64_t)(t0 + k) * sT + cls] * kLog2e : kDead;
+      if (p < Lp) gam[k * Lp + p] = xla[j][k];   // the beta chain reads them in reversed label order
+    }
+  }
+  // ---- 1b. boundary vectors of both directions: every region carries its own frame; re-base on the largest value
+  float2 v[2][P];
+  double refd[2];
+  {
+    double roff[2][P], cand[2];
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+      const size_t vecidx = (size_t)(dir * N + n) * (sc.nblk + 1) + (dir ? (b + 1) : b);
+      const float* brow = sc.bound + vecidx * sc.Sq;
+      const double* boffs = sc.boff + vecidx * sc.G;
+      cand[dir] = -CUDART_INF;
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        v[dir][j] = *reinterpret_cast<const float2*>(brow + p2[j]);
+        roff[dir][j] = boffs[p2[j] / kRegion];
+        const float m = fmaxf(v[dir][j].x, v[dir][j].y);
+        if (m > -1.0e29f) cand[dir] = fmax(cand[dir], roff[dir][j] + (double)m);
+      }
+    }
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cand[dir] = fmax(cand[dir], __shfl_xor_sync(0xffffffffu, cand[dir], o));
+      if (lane == 0) red[dir * 32 + warp] = cand[dir];
+    }
+    __syncthreads();                             // also: lab, nxt, xbs, pads, label emissions are in smem
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+      double ref = -CUDART_INF;
+      for (int w = 0; w < nw; ++w) ref = fmax(ref, red[dir * 32 + w]);
+      if (ref == -CUDART_INF) ref = 0.0;         // nothing alive (infeasible): any offset will do
+      refd[dir] = ref;
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        const float sh = (float)(roff[dir][j] - ref);
+        v[dir][j].x = (v[dir][j].x > -1.0e29f) ? v[dir][j].x + sh : kDead;
+        v[dir][j].y = (v[dir][j].y > -1.0e29f) ? v[dir][j].y + sh : kDead;
+      }
+    }
+  }
+  // ---- 1c. the two chains, one alpha step and one beta step per barrier.
+  // alpha: start vector -> rowsA[0] -> ... -> rowsA[kb-1].  beta (reversed state order): the last frame's row is
+  // emission + betahat (no transition), then rowsB[kb-2] ... rowsB[0].  The alpha start vector borrows rowsB[0],
+  // which beta writes last; with a single frame it gets its own barrier below.
+  bool skipA[P], skipB[P];
+  int qb[P];                                     // label position of this thread's beta pair
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int p = p2[j] >> 1;
+    skipA[j] = (p >= 1 && p < L) && (lab[p - 1] != lab[p]);
+    qb[j] = L - 1 - p;
+    skipB[j] = (p >= 1 && p < L) && (lab[L - p] != lab[L - 1 - p]);
+  }
+  float* initA = rowsB;
+  double offA = refd[0], offB = refd[1];
+  {
+    float vmA = kDead, vmB = kDead;
+    float* firstB = rowsB + (kb - 1) * RS;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      *reinterpret_cast<float2*>(initA + p2[j]) = v[0][j];
+      vmA = fmaxf(vmA, fmaxf(v[0][j].x, v[0][j].y));
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const float xlb = (qb[j] >= 0) ? gam[(kb - 1) * Lp + qb[j]] : kDead;
+      const float2 r = make_float2(xbs[kb - 1] + v[1][j].x, xlb + v[1][j].y);
+      if (kb > 1) *reinterpret_cast<float2*>(firstB + p2[j]) = r;
+      v[1][j] = r;                               // kept for the kb == 1 case
+      vmB = fmaxf(vmB, fmaxf(r.x, r.y));
+    }
+    const int wa = __reduce_max_sync(0xffffffffu, f2ord(vmA));
+    const int wb = __reduce_max_sync(0xffffffffu, f2ord(vmB));
+    if (lane == 0) {
+      wmx[32 + warp] = wa;                       // alpha slot 1: read by step k = 0
+      wmx[64 + warp] = wb;                       // beta slot 0: read by step k = 1
+    }
+    if (tid == 0) offs[K + kb - 1] = offB;
+  }
+  __syncthreads();
+  const float* prevA = initA;
+  const float* prevB = rowsB + (kb - 1) * RS;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    if (k < kb) {
+      // alpha step k (frame t0+k) and beta step k (frame t1-k; k = 0 was the emission-only row)
+      const bool do_b = k >= 1;
+      int mva = (lane < nw) ? wmx[((k + 1) & 1) * 32 + lane] : f2ord(kDead);
+      int mvb = (lane < nw && do_b) ? wmx[64 + ((k + 1) & 1) * 32 + lane] : f2ord(kDead);
+      mva = __reduce_max_sync(0xffffffffu, mva);
+      mvb = __reduce_max_sync(0xffffffffu, mvb);
+      const float ma = ord2f(mva), mb = ord2f(mvb);
+      const float ca = (ma > -1.0e29f) ? ma : 0.0f, cb = (mb > -1.0e29f) ? mb : 0.0f;
+      offA += (double)ca;
+      offB += (double)cb;
+      const int rb = kb - 1 - k;
+      float* curA = rowsA + k * RS;
+      float* curB = rowsB + rb * RS;
+      const float xbA = xbs[k] - ca, xbB = xbs[do_b ? rb : 0] - cb;
+      float vmA = kDead, vmB = kDead;
+      float2 ra[P], rbv[P];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        const float pm1 = prevA[p2[j] - 1];
+        const float2 pp = *reinterpret_cast<const float2*>(prevA + p2[j]);
+        ra[j].x = xbA + lse2_n(pp.x, pm1);
+        ra[j].y = (xla[j][k] - ca) + lse3_n(pp.y, pp.x, skipA[j] ? pm1 : kDead);
+        vmA = fmaxf(vmA, fmaxf(ra[j].x, ra[j].y));
+        if (do_b) {
+          const float qm1 = prevB[p2[j] - 1];
+          const float2 qq = *reinterpret_cast<const float2*>(prevB + p2[j]);
+          const float xlb = (qb[j] >= 0) ? gam[rb * Lp + qb[j]] : kDead;
+          rbv[j].x = xbB + lse2_n(qq.x, qm1);
+          rbv[j].y = (xlb - cb) + lse3_n(qq.y, qq.x, skipB[j] ? qm1 : kDead);
+          vmB = fmaxf(vmB, fmaxf(rbv[j].x, rbv[j].y));
+        }
+      }
+      if (kb == 1) {                             // single frame: beta's row takes the place of the alpha start vector
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < P; ++j) *reinterpret_cast<float2*>(rowsB + p2[j]) = v[1][j];
+      }
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        *reinterpret_cast<float2*>(curA + p2[j]) = ra[j];
+        if (do_b) *reinterpret_cast<float2*>(curB + p2[j]) = rbv[j];
+      }
+      const int wa = __reduce_max_sync(0xffffffffu, f2ord(vmA));
+      const int wb = __reduce_max_sync(0xffffffffu, f2ord(vmB));
+      if (lane == 0) {
+        wmx[(k & 1) * 32 + warp] = wa;
+        if (do_b) wmx[64 + (k & 1) * 32 + warp] = wb;
+      }
+      if (tid == 0) {
+        offs[k] = offA;
+        if (do_b) offs[K + rb] = offB;
+      }
+      prevA = curA;
+      if (do_b) prevB = curB;
+      __syncthreads();
+    }
+  }
+
+  if (!dense_first) dense();
+  __syncthreads();                               // dense stores of every thread precede the sparse overwrite
+
+  // ---- 2. occupancies and the sparse correction (gam: label emissions are replaced by label occupancies)
+  const double ll2 = sc.ll2[n];
+  float bs[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    bs[k] = 0.0f;
+    if (k < kb) {
+      const float kt = (float)(offs[k] + offs[K + k] - ll2);
+      const float* arow = rowsA + k * RS;
+      const float* brw = rowsB + k * RS;
+      const float xbk = xbs[k];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        const int sb = p2[j];                      // blank state 2p, label state 2p+1
+        if (sb < S) bs[k] += fast_ex2((arow[sb] + brw[S - 1 - sb]) + (kt - xbk));
+      }
+    }
+    bs[k] = warp_sum(bs[k]);
+    if (lane == 0) bsum_s[warp * K + k] = bs[k];
+  }
+  __syncthreads();                               // every beta step has read its emissions from gam
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    if (k < kb) {
+      const float kt = (float)(offs[k] + offs[K + k] - ll2);
+      const float* arow = rowsA + k * RS;
+      const float* brw = rowsB + k * RS;
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        const int sb = p2[j];
+        if (sb + 1 < S) gam[k * Lp + (sb >> 1)] = fast_ex2((arow[sb + 1] + brw[S - 2 - sb]) + (kt - xla[j][k]));
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int q = p2[j] >> 1;
+    if (lead_q[j]) {
+      float acc[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = 0.0f;
+      for (int m = q; m >= 0; m = nxt[m]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] += gam[k * Lp + m];
+      }
+      const int c = lab[q];
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (k < kb) grad[((int64_t)(t0 + k) * N + n) * C + c] = (fast_ex2(xla[j][k]) - acc[k]) * g;
+    }
+  }
+  if (tid < kb) {
+    float sacc = 0.0f;
+    for (int w = 0; w < nw; ++w) sacc += bsum_s[w * K + tid];
+    grad[((int64_t)(t0 + tid) * N + n) * C + blank] = (fast_ex2(xbs[tid]) - sacc) * g;
+  }
+}
+
+template <int P, int MAXT, int MINB>
+static int launch_block_grad(int NTc, cudaStream_t st, int N, const float* lp, int64_t sT, int64_t sN, int T, int C,
+                             const int64_t* tgt, int64_t tgt_stride, int Lmax, const int64_t* in_len,
+                             const int64_t* tgt_len, int blank, const float* gout, int64_t gout_stride, float* grad,
+                             const CtcScratch& sc, const BgSmem& lay, int vec) {
+  auto kern = ctc_block_grad_kernel<P, kBlkK, MAXT, MINB>;
+  DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+  kern<<<dim3(sc.nblk, N), NTc, lay.total, st>>>(lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, gout,
+                                                 gout_stride, grad, sc, lay, vec);
+  DAE_LAUNCH_OK();
+  return 0;
+}
+
+// Gradient of the blocked path.  Returns 1 when the shape does not fit the fused kernel's shared memory (the
+// caller then runs ctc_fill_kernel + ctc_grad_kernel).
+int ctc_blocked_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
+                     int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank,
+                     const float* gout, int64_t gout_stride, float* grad, const CtcScratch& sc, int vec,
+                     cudaStream_t st) {
+  int P, NTc;
+  lat_geometry(Lmax, P, NTc);
+  const BgSmem lay = bg_smem_layout(sc.Lp, sc.Sp, kBlkK);
+  if (lay.total > 110 * 1024) {                  // two CTAs per SM or not at all
+    int rc = ctc_blocked_fill(lp, sT, sN, T, N, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, sc, st);
+    return rc ? rc : 1;
+  }
+#define DAE_BG(PP, MT, MB)                                                                                         \
+  return launch_block_grad<PP, MT, MB>(NTc, st, N, lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, \
+                                       gout, gout_stride, grad, sc, lay, vec)
+  constexpr int kMaxC = kLatThreads - 64;
+  if (P <= 1 && NTc <= 640) DAE_BG(1, 640, 2);
+  if (P <= 1) DAE_BG(1, kMaxC, 1);
+  if (P <= 2) DAE_BG(2, kMaxC, 1);
+  DAE_BG(4, kMaxC, 1);
+#undef DAE_BG
+}
+
 int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
                         int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank,
                         float* nll, const CtcScratch& sc, cudaStream_t st) {
@@ -663,17 +1040,7 @@ int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, i
   DAE_LAUNCH_OK();
   ctc_boundary_kernel<kBlkK><<<dim3(sc.G, 2, N), kBndThreads, 0, st>>>(T, Lmax, in_len, tgt_len, nll, sc);
   DAE_LAUNCH_OK();
-  int P, NTc;
-  lat_geometry(Lmax, P, NTc);
-#define DAE_FILL(PP, MT, MB) \
-  return launch_fill<PP, MT, MB>(NTc, st, N, lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, sc)
-  constexpr int kMaxC = kLatThreads - 64;
-  if (P <= 1 && NTc <= 320) DAE_FILL(1, 320, 4);       // short label sequences: several blocks per SM
-  if (P <= 1 && NTc <= 640) DAE_FILL(1, 640, 2);
-  if (P <= 1) DAE_FILL(1, kMaxC, 1);
-  if (P <= 2) DAE_FILL(2, kMaxC, 1);
-  DAE_FILL(4, kMaxC, 1);
-#undef DAE_FILL
+  return 0;
 }
 
 }  // namespace dae

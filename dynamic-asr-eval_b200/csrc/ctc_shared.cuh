@@ -173,4 +173,13 @@ int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, i
                         int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank,
                         float* nll, const CtcScratch& sc, cudaStream_t st);
 
+int ctc_blocked_fill(const float* lp, int64_t sT, int64_t sN, int T, int N, const int64_t* tgt, int64_t tgt_stride,
+                     int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank, const CtcScratch& sc,
+                     cudaStream_t st);
+// returns 0 when the gradient has been written, 1 when only alpha/beta rows were filled (run ctc_grad_kernel next)
+int ctc_blocked_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
+                     int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank,
+                     const float* gout, int64_t gout_stride, float* grad, const CtcScratch& sc, int vec,
+                     cudaStream_t st);
+
 }  // namespace dae

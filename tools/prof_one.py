@@ -48,9 +48,15 @@ def main():
             s.record()
             loss = f(x, tg, il, tl)
             e.record()
-            (loss / T).backward()
+            scaled = loss / T
+            s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(600000)           # keep the GPU busy (no memory traffic) while the CPU queues the backward
+            s2.record()
+            scaled.backward()
+            e2.record()
             torch.cuda.synchronize()
-            print("lattice ms", s.elapsed_time(e), "loss", loss.item())
+            print("lattice ms", s.elapsed_time(e), "backward ms (incl. torch autograd glue)", s2.elapsed_time(e2),
+                  "loss", loss.item())
     elif a.what == "greedy":
         from dae.greedy import greedy_ids_device
         lp = peaky(52000, 4096, 4095, g)

@@ -757,20 +757,15 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
   // half of the grid streams first and runs its chains later, the other half the other way round, so the two
   // CTAs that share an SM overlap memory traffic with the latency-bound chains
   const bool dense_first = (int)blockIdx.x * 2 < (int)gridDim.x || kb == 0;
-  if (dense_first) dense();
-  if (kb == 0) return;
+  if (kb == 0) {
+    dense();
+    return;
+  }
 
-  // ---- 1a. labels, list links, emissions of the block's frames at every label state
+  // ---- 1a. labels, list links, emissions of the block's frames at every label state.  All global loads of the
+  // prologue are issued before the dense stream starts, so their latency hides behind it.
   const int t1 = t0 + kb - 1;
-  for (int k = tid; k < L; k += NTc) {
-    lab[k] = (int)tgt[n * tgt_stride + k];
-    nxt[k] = sc.next_same[(int64_t)n * Lp + k];
-  }
-  for (int r = tid; r < 4 * 2 * K; r += NTc) {
-    float* row = (r < 4 * K) ? rowsA + (r >> 2) * RS : rowsB + ((r >> 2) - K) * RS;
-    row[(r & 3) - 4] = kDead;
-  }
-  if (tid < K) xbs[tid] = (tid < kb) ? base[(int64_t)(t0 + tid) * sT + blank] * kLog2e : kDead;
+  const double ll2 = sc.ll2[n];
   int p2[P];
   bool lead_q[P];
   float xla[P][K];                               // emissions (log2) of this thread's label states, per frame
@@ -781,10 +776,26 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
     lead_q[j] = (p < L) ? (sc.leader[(int64_t)n * Lp + p] != 0) : false;
     const int cls = (p < L) ? (int)tgt[n * tgt_stride + p] : blank;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < K; ++k)
       xla[j][k] = (k < kb && p < L) ? base[(int64_t)(t0 + k) * sT + cls] * kLog2e : kDead;
+  }
+  const float xb_mine = (tid < kb) ? base[(int64_t)(t0 + tid) * sT + blank] * kLog2e : kDead;
+  if (dense_first) dense();
+  for (int k = tid; k < L; k += NTc) {
+    lab[k] = (int)tgt[n * tgt_stride + k];
+    nxt[k] = sc.next_same[(int64_t)n * Lp + k];
+  }
+  for (int r = tid; r < 4 * 2 * K; r += NTc) {
+    float* row = (r < 4 * K) ? rowsA + (r >> 2) * RS : rowsB + ((r >> 2) - K) * RS;
+    row[(r & 3) - 4] = kDead;
+  }
+  if (tid < K) xbs[tid] = xb_mine;
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int p = tid + j * NTc;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
       if (p < Lp) gam[k * Lp + p] = xla[j][k];   // the beta chain reads them in reversed label order
-    }
   }
   // ---- 1b. boundary vectors of both directions: every region carries its own frame; re-base on the largest value
   float2 v[2][P];
@@ -933,7 +944,6 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
   __syncthreads();                               // dense stores of every thread precede the sparse overwrite
 
   // ---- 2. occupancies and the sparse correction (gam: label emissions are replaced by label occupancies)
-  const double ll2 = sc.ll2[n];
   float bs[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {

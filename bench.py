@@ -312,7 +312,7 @@ def run_dae(a, rank, world, local):
         roof = {"kernel": "ctc_lattice+ctc_grad (CTC loss+grad of one adapt step, T=2048 N=1 C=4096)", "bound": "hbm",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "avg_launch_us": t_pair * 1e3,
-                "note": "N=1 lattice is a 2048-step dependent chain (latency-bound); see DESIGN.md"}
+                "note": "N=1: time-blocked lattice (transfer bands + 256-step boundary scan + fused block gradient); the scan is a dependent chain (latency-bound); see DESIGN.md"}
     cpu = cpu_baseline_sample(a.frames) if world == 1 else None
     aux = aux_kernels(peak) if (world == 1 and not a.no_aux) else None
     line = {

@@ -7,7 +7,7 @@ TAG=${1:-r01}; shift
 FAMS=${@:-ctc greedy specaug stitch softdtw beam}
 O=gpurun_out
 mkdir -p $O
-KRE='regex:ctc_|argmax_rows|collapse_kernel|specaug_|stitch_kernel|softdtw_|beam_search'
+KRE='regex:ctc_|argmax_rows|collapse_kernel|specaug_|stitch_kernel|softdtw_|beam_search|cutout_|ngram_'
 for fam in $FAMS; do
   timeout 300 python tools/prof_one.py $fam --reps 2 > $O/plain_$fam.log 2>&1 || { echo "plain run of $fam failed"; tail -5 $O/plain_$fam.log; exit 1; }
 done
@@ -17,7 +17,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" 
     --log-file $O/launches_${TAG}.csv python bench.py --steps 1 --warmup 1 --frames 40000 --no-aux > $O/ncu_bench.log 2>&1
 echo "launch list rc=$?"
 for fam in $FAMS; do
-  timeout 420 ncu --set full --clock-control none --import-source on -k "$KRE" -c 4 -f -o $O/${fam}_${TAG} \
+  timeout 420 ncu --set full --clock-control none --import-source on -k "$KRE" -c 8 -f -o $O/${fam}_${TAG} \
       python tools/prof_one.py $fam --reps 1 > $O/ncu_$fam.log 2>&1
   echo "$fam rc=$?"
 done

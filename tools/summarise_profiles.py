@@ -80,12 +80,18 @@ def main():
             w.writerow({c: r.get(c, "") for c in cols})
     # traffic of the CTC pair (per launch, DRAM read+write)
     traffic = {}
-    lat = [r for r in all_rows if "ctc_lattice" in r["kernel"]]
-    grd = [r for r in all_rows if "ctc_grad" in r["kernel"]]
-    if lat and grd:
-        tb = (lat[-1].get("dram_read_MB", 0) + lat[-1].get("dram_write_MB", 0) + grd[-1].get("dram_read_MB", 0) +
-              grd[-1].get("dram_write_MB", 0)) * 1e6
+    # one CTC loss+grad = every ctc_* launch of one repetition (bands + scan + fused block gradient, or the
+    # per-frame chain + row gradient when that path is active)
+    ctc = [r for r in all_rows if r["family"] == "ctc" and "ctc_" in r["kernel"]]
+    if ctc:
+        seen, tb = set(), 0.0
+        for r in ctc:
+            if r["kernel"] in seen:
+                continue
+            seen.add(r["kernel"])
+            tb += (r.get("dram_read_MB", 0) + r.get("dram_write_MB", 0)) * 1e6
         traffic["ctc_lattice+ctc_grad"] = tb
+        traffic["ctc_kernels"] = sorted(seen)
     for r in all_rows:
         traffic.setdefault("per_kernel", {})[r["family"] + ":" + r["kernel"]] = (r.get("dram_read_MB", 0) + r.get("dram_write_MB", 0)) * 1e6
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)

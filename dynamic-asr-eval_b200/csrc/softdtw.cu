@@ -249,6 +249,15 @@ softdtw_wave_kernel(SdtwParams P, int vec, int smem_per_warp) {
             if (BWD) { nx_r[us] = __ldcg(upR + (M - 1 - col2)); nx_d[us] = __ldcg(upD + (M - 1 - col2)); }
           }
         }
+        // inputs of the next kGrp cells leave shared memory before the dependent chain starts
+        float dq[kGrp], rq[kGrp];
+#pragma unroll
+        for (int q = 0; q < kGrp; ++q) {
+          const int sc = ((j + q) & (kRingCols - 1)) ^ flipx;
+          dq[q] = sDl[sc];
+          rq[q] = BWD ? sRl[sc] : 0.0f;
+        }
+        float pub[kGrp];
 #pragma unroll
         for (int q = 0; q < kGrp; ++q, ++p, ++j) {
           // upper neighbour: the upper lane's latest cell (its column equals ours); lane 0 takes the band above
@@ -259,8 +268,7 @@ softdtw_wave_kernel(SdtwParams P, int vec, int smem_per_warp) {
             const float a_w = BWD ? __shfl_sync(0xffffffffu, ab_w, q) : 0.0f;
             if (lane == 0) { nu_v = a_v; nu_w = a_w; }
           }
-          const int sc = (j & (kRingCols - 1)) ^ flipx;
-          const float d = sDl[sc];
+          const float d = dq[q];
           const bool active = row_ok && (unsigned)j < (unsigned)M;
           float res_v, res_w = 0.0f;
           if (!BWD) {
@@ -274,7 +282,7 @@ softdtw_wave_kernel(SdtwParams P, int vec, int smem_per_warp) {
             }
           } else {
             // E = E_dn*a + E_right*b + E_diag*c, a,b,c = exp((W[.] - R[i,j]) / gamma)  (:100-108)
-            float r = sRl[sc];
+            float r = rq[q];
             if (PRUNE && isinf(r)) r = -INF;                 // :96-97 (only pruned cells hold +inf)
             res_w = r - d;
             const float a = ex2f_((nu_w - r) * ig2), bb = ex2f_((my_w - r) * ig2), c = ex2f_((up_w - r) * ig2);
@@ -288,8 +296,17 @@ softdtw_wave_kernel(SdtwParams P, int vec, int smem_per_warp) {
           if (active) {
             my_v = res_v; my_w = res_w;
             sOl[(j & (kOutCols - 1)) ^ flipx] = res_v;
-            // publish the band's bottom row for the band below: {value, column+1} in one 8-byte store
-            if (publish) st_volatile_int2(exp_mine + j, make_int2(__float_as_int(res_v), j + 1));
+          }
+          pub[q] = res_v;
+        }
+        // publish the band's bottom row for the band below: {value, column+1} in one 8-byte store per cell, after
+        // the group so that the volatile stores do not fence the chain's shared-memory traffic
+        if (publish) {
+#pragma unroll
+          for (int q = 0; q < kGrp; ++q) {
+            const int jq = j - kGrp + q;
+            if ((unsigned)jq < (unsigned)M && row_ok)
+              st_volatile_int2(exp_mine + jq, make_int2(__float_as_int(pub[q]), jq + 1));
           }
         }
       }

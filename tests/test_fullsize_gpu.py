@@ -63,6 +63,42 @@ def test_ctc_batch_of_64_properties(cuda):
     assert x.grad[:1500, 3].abs().sum() > 0
 
 
+def test_ctc_adapt_step_blocked_equals_chain(cuda, monkeypatch):
+    """The adapt step's shape ([2048, N, 4096], N = 1 and a ragged N = 2 as in AWMC): the time-blocked lattice
+    (default for few samples) and the per-frame chain are two implementations of the same function: losses agree
+    to 1e-6 relative, gradients within the 1e-4 elementwise tolerance, gradient rows sum to zero, padding frames are zero."""
+    from dae.ctc import ctc_loss
+    from dae.greedy import greedy_ids_device
+    T, C = 2048, 4096
+    for N, in_lens in ((1, [T]), (2, [T, T - 333])):
+        post = torch.stack([_peaky_gpu(T, C, C - 1, 300 + n) for n in range(N)], 1)
+        labs = []
+        for n in range(N):
+            _, ids, k = greedy_ids_device(post[:in_lens[n], n], C - 1)
+            labs.append(ids[0, :int(k[0])].long())
+        Lmax = max(int(l.numel()) for l in labs)
+        tg = torch.zeros(N, Lmax, dtype=torch.long, device="cuda")
+        for n, l in enumerate(labs):
+            tg[n, :l.numel()] = l
+        il = torch.tensor(in_lens, device="cuda")
+        tl = torch.tensor([int(l.numel()) for l in labs], device="cuda")
+        out = {}
+        for path in ("0", "1"):
+            monkeypatch.setenv("DAE_CTC_BLOCKED", path)
+            x = post.clone().requires_grad_()
+            nll = ctc_loss(x, tg, il, tl, blank=C - 1, reduction="none")
+            (nll.sum() / T).backward()
+            out[path] = (nll.detach().reshape(-1), x.grad)
+        (nll_c, g_c), (nll_b, g_b) = out["0"], out["1"]
+        assert torch.allclose(nll_b, nll_c, rtol=1e-6, atol=0)
+        # north_star tolerance (each term of g*(exp(lp) - occupancy) good to 1e-4 relative), as in test_kernels_gpu
+        tol = 1e-4 * g_c.abs() + 1e-4 * (1.0 / T) * post.exp() + 1e-12
+        assert float(((g_b - g_c).abs() / tol).max()) <= 1.0
+        assert float(g_b.sum(-1).abs().max()) <= 1e-6          # sum_c exp(lp) = 1 = sum_c occupancy
+        for n in range(N):
+            assert torch.all(g_b[in_lens[n]:, n] == 0)
+
+
 def test_stitch_recording_sized(cuda):
     """52 windows x [2048, 4096] (1.7 GB): rows are probability distributions, rows covered by one window are
     that window's rows, fused argmax == argmax of the output."""

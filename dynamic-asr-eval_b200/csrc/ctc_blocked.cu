@@ -162,8 +162,9 @@ ctc_xfer_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, con
 
 // ------------------------------------------------------------------------------------------ 2. boundary scan
 constexpr int kBndStages = 4;                     // transfer-band prefetch depth (steps)
-constexpr int kTermsPerThread = kBlkK + 1;        // two threads share the 2K+1 terms of a destination state
-constexpr int kBndThreads = 2 * kRegion + 96;     // consumers + band-prefetch, hand-over and frame warps
+constexpr int kTpd = 2;                           // consumer threads per destination state (4: slower, 1: no shuffles but 2x the stream)
+constexpr int kTermsPerThread = (2 * kBlkK + 1 + kTpd - 1) / kTpd;   // they share the 2K+1 terms of the state
+constexpr int kBndThreads = kTpd * kRegion + 96;  // consumers + band-prefetch, hand-over and frame warps
 
 // grid (G, 2, N): region g of direction dir (0 alpha, 1 beta in reversed state order u = S-1-s) of sample n.
 // Two consumer threads per destination state and three helper warps, all meeting at one barrier per step:
@@ -187,9 +188,9 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
   __shared__ uint64_t full[kBndStages];
   const int g = blockIdx.x, dir = blockIdx.y, n = blockIdx.z, N = gridDim.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool consumer = tid < 2 * kRegion;
-  const bool tma_warp = warp == 2 * kRegion / 32, halo_warp = warp == 2 * kRegion / 32 + 1,
-             frame_warp = warp == 2 * kRegion / 32 + 2;
+  const bool consumer = tid < kTpd * kRegion;
+  const bool tma_warp = warp == kTpd * kRegion / 32, halo_warp = warp == kTpd * kRegion / 32 + 1,
+             frame_warp = warp == kTpd * kRegion / 32 + 2;
   int Tn, L;
   clamp_lengths(in_len, tgt_len, n, T, Lmax, Tn, L);
   const int S = 2 * L + 1;
@@ -209,7 +210,7 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
   int2* halo0 = sc.halo + vec0 * G * kHaloWords;
   const float* xf0 = sc.xfer + (size_t)n * sc.nblk * Sq * W;
   const int u0 = g * kRegion;
-  const int i = (tid >> 1) & (kRegion - 1), h = tid & 1;
+  const int i = (tid / kTpd) & (kRegion - 1), h = tid % kTpd;
   const int u = u0 + i;
 
   // Band rows this region reads each step, as one contiguous chunk of xfer[b]:
@@ -405,7 +406,7 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
     pp[k] = &buf[0][po];
     hmask[k] = (valid && po < H) ? 1.0f : 0.0f;
   }
-  const bool uses_halo = warp == 0;              // destinations 0..15 of the region reach below it
+  const bool uses_halo = i < H;                  // destinations 0..2K-1 of the region reach below it (whole warps)
   const int64_t vstep = dir ? -1 : 1;            // boundary vector index advance per step
   float* bout = brow0 + (size_t)(dir ? (nb - 1) : 1) * Sq + u;
   int2* hout = halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + g) * kHaloWords + (i - (kRegion - H));
@@ -425,16 +426,16 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
       _Pragma("unroll") for (int k = 0; k < kTermsPerThread; ++k)                                          \
         term[k] = xp[k][(SLOT) * CH] + pp[k][(PAR) * BS];                                                  \
     }                                                                                                      \
-    float mx = fmaxf(fmaxf(term[0], term[1]), term[2]);                                                    \
-    _Pragma("unroll") for (int k = 3; k < kTermsPerThread; ++k) mx = fmaxf(mx, term[k]);                   \
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));                                                   \
+    float mx = term[0];                                                                                    \
+    _Pragma("unroll") for (int k = 1; k < kTermsPerThread; ++k) mx = fmaxf(mx, term[k]);                   \
+    _Pragma("unroll") for (int o = 1; o < kTpd; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); \
     float s0 = 0.0f, s1 = 0.0f;                                                                            \
     _Pragma("unroll") for (int k = 0; k < kTermsPerThread; ++k) {                                          \
       const float e = fast_ex2(term[k] - mx);                                                              \
       if (k & 1) s1 += e; else s0 += e;                                                                    \
     }                                                                                                      \
     float sum = s0 + s1;                                                                                   \
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);                                                           \
+    _Pragma("unroll") for (int o = 1; o < kTpd; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);   \
     float val = mx + fast_lg2(sum);                                                                        \
     if (!uses_halo) val += osh;                                                                            \
     if (forced_dead) val = kDead;                                                                          \

@@ -18,17 +18,19 @@
 //                           boundary vector, written in the scratch layout ctc_grad_kernel reads.
 // Values are log2 units with the finite dead-state sentinel of ctc_shared.cuh; every region / row carries an
 // fp64 offset so stored fp32 values stay O(1).
+#include <cooperative_groups.h>
 #include "ctc_shared.cuh"
 
 namespace dae {
 
+// generic address space: the word lives in global memory or in the shared memory of a CTA of the same cluster
 __device__ __forceinline__ int2 ld_tagged(const int2* p) {
   int2 v;
-  asm volatile("ld.volatile.global.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  asm volatile("ld.volatile.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_tagged(int2* p, int2 v) {
-  asm volatile("st.volatile.global.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+  asm volatile("st.volatile.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 __device__ __forceinline__ void cp_async_f32(float* dst_smem, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
@@ -188,6 +190,22 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
   __shared__ uint64_t full[kBndStages];
   const int g = blockIdx.x, dir = blockIdx.y, n = blockIdx.z, N = gridDim.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Hand-over inside a thread-block cluster goes through the receiver's shared memory (DSMEM): the region below
+  // writes its tagged words straight into this mailbox and the hand-over warp polls locally.  Regions at a
+  // cluster boundary (and launches without clusters) use the global mailbox.
+  extern __shared__ __align__(16) int2 mbox[];          // [nblk+1][kHaloWords], slot = vector number
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  if (CL > 1) {
+    for (int k = tid; k < (sc.nblk + 1) * kHaloWords; k += blockDim.x) mbox[k] = make_int2(0, 0);
+    cluster.sync();
+  }
+  if (g >= sc.G) return;                                // grid padded to whole clusters
+  const bool up_local = CL > 1 && crank > 0 && g > 0;
+  const bool down_local = CL > 1 && crank + 1 < CL && g + 1 < sc.G;
+  int2* mbox_down = down_local ? cluster.map_shared_rank(mbox, crank + 1) : nullptr;
   const bool consumer = tid < kTpd * kRegion;
   const bool tma_warp = warp == kTpd * kRegion / 32, halo_warp = warp == kTpd * kRegion / 32 + 1,
              frame_warp = warp == kTpd * kRegion / 32 + 2;
@@ -285,8 +303,9 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
   if (halo_warp) {
     // ------------------------------------------------------------------------------ hand-over from region g-1
     // Fetches the 2K values, the frame and the maximum of the halo of V_{st+1} while the consumers work on step st.
-    const int64_t pstep = (dir ? -1 : 1) * (int64_t)G * kHaloWords;
-    const int2* hp = halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + (g > 0 ? g - 1 : 0)) * kHaloWords + lane;
+    const int64_t pstep = up_local ? (int64_t)kHaloWords : (dir ? -1 : 1) * (int64_t)G * kHaloWords;
+    const int2* hp = up_local ? (mbox + kHaloWords + lane)
+                              : (halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + (g > 0 ? g - 1 : 0)) * kHaloWords + lane);
     const bool polls = g > 0 && lane < kHaloWords;
     // Words are requested two steps before they are consumed (one L2 round trip is longer than a step); the
     // region below runs ahead by that much once the pipeline has filled.
@@ -328,7 +347,9 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
     // in are shifted by one step's drift only.
     const int64_t vstep = dir ? -1 : 1;
     double* bo = boff0 + (size_t)(dir ? (nb - 1) : 1) * G + g;          // frame of V_1
-    int2* ho_words = halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + g) * kHaloWords + H + (lane & 1);
+    int2* ho_words = (down_local ? (mbox_down + kHaloWords) : (halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + g) * kHaloWords)) +
+                     H + (lane & 1);
+    const int64_t ho_step = down_local ? (int64_t)kHaloWords : vstep * G * kHaloWords;
     const bool pub = g + 1 < G && lane < 2;
     // Frames are fp64 sums of fp32 steps; all decisions are made on small fp32 quantities relative to the
     // newest frame F1 = F(st+1), so the per-step chain is a dozen fp32 instructions and two fp64 adds.
@@ -370,7 +391,7 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
       hmp = hm; hrelp = hrel - delta; halo_had = halo_alive;     // relative to F2, the next step's F1
       if (st + 1 < nb) {
         bo += vstep * G;
-        ho_words += vstep * G * kHaloWords;
+        ho_words += ho_step;
         if (lane == 0) {
           oshift[(st + 1) & 1] = -delta;
           Fd[(st + 1) & 1] = F2;
@@ -409,7 +430,9 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
   const bool uses_halo = i < H;                  // destinations 0..2K-1 of the region reach below it (whole warps)
   const int64_t vstep = dir ? -1 : 1;            // boundary vector index advance per step
   float* bout = brow0 + (size_t)(dir ? (nb - 1) : 1) * Sq + u;
-  int2* hout = halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + g) * kHaloWords + (i - (kRegion - H));
+  int2* hout = (down_local ? (mbox_down + kHaloWords) : (halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + g) * kHaloWords)) +
+               (i - (kRegion - H));
+  const int64_t hout_step = down_local ? (int64_t)kHaloWords : vstep * G * kHaloWords;
   const bool pub_val = h == 0 && i >= kRegion - H && g + 1 < G;
   constexpr int BS = H + kRegion + 2;            // buffer stride
   __syncthreads();                               // "start"
@@ -445,7 +468,7 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
     }                                                                                                      \
     if (pub_val) st_tagged(hout, make_int2(__float_as_int(val), st + 1));                                  \
     bout += vstep * Sq;                                                                                    \
-    hout += vstep * G * kHaloWords;                                                                        \
+    hout += hout_step;                                                                                     \
     ++st;                                                                                                  \
     __syncthreads();                                                                                       \
   }
@@ -1049,8 +1072,32 @@ int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, i
   ctc_xfer_kernel<kBlkK><<<dim3(sc.nblk, tiles, N), kXferTile, 0, st>>>(lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len,
                                                                        tgt_len, blank, sc);
   DAE_LAUNCH_OK();
-  ctc_boundary_kernel<kBlkK><<<dim3(sc.G, 2, N), kBndThreads, 0, st>>>(T, Lmax, in_len, tgt_len, nll, sc);
-  DAE_LAUNCH_OK();
+  {
+    // clusters of up to 8 regions hand over through DSMEM when the per-step mailbox fits in shared memory
+    const size_t mbox_bytes = (size_t)(sc.nblk + 1) * kHaloWords * sizeof(int2);
+    const char* env = getenv("DAE_CTC_CLUSTER");
+    int cl = env ? atoi(env) : 8;
+    if (cl < 1 || cl > 8 || (cl & (cl - 1))) cl = 8;
+    if (mbox_bytes > 96 * 1024 || sc.G < 2) cl = 1;
+    while (cl > sc.G) cl >>= 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((sc.G + cl - 1) / cl * cl, 2, N);
+    cfg.blockDim = dim3(kBndThreads);
+    cfg.dynamicSmemBytes = cl > 1 ? mbox_bytes : 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cfg.dynamicSmemBytes > 24 * 1024)
+      DAE_CUDA(cudaFuncSetAttribute(ctc_boundary_kernel<kBlkK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)cfg.dynamicSmemBytes));
+    DAE_CUDA(cudaLaunchKernelEx(&cfg, ctc_boundary_kernel<kBlkK>, T, Lmax, in_len, tgt_len, nll, sc));
+    DAE_LAUNCH_OK();
+  }
   return 0;
 }
 

@@ -98,6 +98,13 @@ ctc_xfer_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, con
   __shared__ unsigned char skp[EW];              // 1: state s0+j may be entered from s0+j-2
   __shared__ __align__(16) float outs[kXferTile * W];
   const int b = blockIdx.x, s0 = blockIdx.y * kXferTile, n = blockIdx.z, tid = threadIdx.x;
+  {
+    // the scan's global hand-over words are matched by tag (step number): they start from zero on every call
+    const size_t n_words = (size_t)2 * gridDim.z * (sc.nblk + 1) * sc.G * kHaloWords;
+    const size_t n_thr = (size_t)gridDim.x * gridDim.y * gridDim.z * kXferTile;
+    const size_t me = ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * kXferTile + tid;
+    for (size_t w = me; w < n_words; w += n_thr) sc.halo[w] = make_int2(0, 0);
+  }
   int Tn, L;
   clamp_lengths(in_len, tgt_len, n, T, Lmax, Tn, L);
   const int S = 2 * L + 1;
@@ -1066,8 +1073,6 @@ int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, i
                         int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank,
                         float* nll, const CtcScratch& sc, cudaStream_t st) {
   (void)C;
-  // hand-over words are matched by tag (step number), so they start from zero on every call
-  DAE_CUDA(cudaMemsetAsync(sc.halo, 0, (size_t)2 * N * (sc.nblk + 1) * sc.G * kHaloWords * sizeof(int2), st));
   const int tiles = (sc.Sq + kXferTile - 1) / kXferTile;
   ctc_xfer_kernel<kBlkK><<<dim3(sc.nblk, tiles, N), kXferTile, 0, st>>>(lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len,
                                                                        tgt_len, blank, sc);

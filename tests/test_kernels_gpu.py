@@ -112,11 +112,13 @@ def test_specaug_plain_call_and_determinism(cuda):
 
 
 # ---------------------------------------------------------------- CTC
-@pytest.fixture(params=["chain", "blocked"])
+@pytest.fixture(params=["chain", "blocked", "blocked_nocluster"])
 def ctc_path(request, monkeypatch):
     """Both lattice implementations behind dae_ctc_lattice: the per-frame chain (ctc.cu) and the time-blocked
-    scan (ctc_blocked.cu); DAE_CTC_BLOCKED forces one or the other regardless of shape."""
-    monkeypatch.setenv("DAE_CTC_BLOCKED", "1" if request.param == "blocked" else "0")
+    scan (ctc_blocked.cu), the latter with hand-over through cluster shared memory (default) and through global
+    memory only; DAE_CTC_BLOCKED / DAE_CTC_CLUSTER force the choice regardless of shape."""
+    monkeypatch.setenv("DAE_CTC_BLOCKED", "0" if request.param == "chain" else "1")
+    monkeypatch.setenv("DAE_CTC_CLUSTER", "1" if request.param == "blocked_nocluster" else "8")
     return request.param
 
 

@@ -763,17 +763,22 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
   // before any is stored, so a thread keeps K independent 128-bit loads in flight.
   auto dense = [&]() {
     if (vec) {
+      constexpr int KH = K / 2;                    // two half batches: K/2 independent 128-bit loads in flight
       for (int i = tid; i < (C >> 2); i += NTc) {
-        float4 v4[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-          if (k < kb) v4[k] = __ldcs(reinterpret_cast<const float4*>(base + (int64_t)(t0 + k) * sT) + i);
+        for (int hb = 0; hb < 2; ++hb) {
+          float4 v4[KH];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          if (k < krows) {
-            float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < kb) o4 = make_float4(__expf(v4[k].x) * g, __expf(v4[k].y) * g, __expf(v4[k].z) * g, __expf(v4[k].w) * g);
-            __stcs(reinterpret_cast<float4*>(grad + ((int64_t)(t0 + k) * N + n) * C) + i, o4);
+          for (int k = 0; k < KH; ++k)
+            if (hb * KH + k < kb) v4[k] = __ldcs(reinterpret_cast<const float4*>(base + (int64_t)(t0 + hb * KH + k) * sT) + i);
+#pragma unroll
+          for (int k = 0; k < KH; ++k) {
+            const int kk = hb * KH + k;
+            if (kk < krows) {
+              float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (kk < kb) o4 = make_float4(__expf(v4[k].x) * g, __expf(v4[k].y) * g, __expf(v4[k].z) * g, __expf(v4[k].w) * g);
+              __stcs(reinterpret_cast<float4*>(grad + ((int64_t)(t0 + kk) * N + n) * C) + i, o4);
+            }
           }
         }
       }

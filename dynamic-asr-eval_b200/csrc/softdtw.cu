@@ -24,7 +24,7 @@ namespace dae {
 
 constexpr int kBand = 32;                 // rows per warp
 constexpr int kTile = 32;                 // columns per staged tile
-constexpr int kGrp = 4;                   // columns per export poll group
+constexpr int kGrp = 8;                   // columns per export poll group
 constexpr int kDepth = 1;                 // groups between requesting band-above values and using them
 constexpr float kLog2eF = 1.4426950408889634f;
 constexpr float kLn2F = 0.6931471805599453f;

@@ -24,7 +24,9 @@ namespace dae {
 
 constexpr int kBand = 32;                 // rows per warp
 constexpr int kTile = 32;                 // columns per staged tile
-constexpr int kGrp = 8;                   // columns per export poll group
+// columns per export poll group: the group head (poll, prefetch, smem reads) is amortised over the group, the band
+// below trails by a few more steps; measured best at 8 forward and 16 backward ([8,4096,4096])
+constexpr int kGrpFwd = 8, kGrpBwd = 16;
 constexpr int kDepth = 1;                 // groups between requesting band-above values and using them
 constexpr float kLog2eF = 1.4426950408889634f;
 constexpr float kLn2F = 0.6931471805599453f;
@@ -138,6 +140,7 @@ template <bool BWD, bool PRUNE>
 __global__ void __launch_bounds__(256)
 softdtw_wave_kernel(SdtwParams P, int vec, int smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kGrp = BWD ? kGrpBwd : kGrpFwd;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* sm = reinterpret_cast<float*>(smem_raw + (size_t)warp * smem_per_warp);
   float* sD = sm;                                            // [32][128]

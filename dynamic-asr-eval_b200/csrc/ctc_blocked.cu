@@ -1,21 +1,28 @@
-// Time-blocked CTC lattice for few samples and many frames (the dynamic-eval adapt step: N=1, T=2048).
-// Same contract as ctc_lattice_kernel (ctc.cu): fills alpha, beta_rev, offsets, label groups, ll2 and nll
-// (torch.nn.CTCLoss semantics; call sites lcasr/lib.py:492,570-579).
+// Time-blocked CTC loss + gradient for few samples and many frames (the dynamic-eval adapt step: N=1, T=2048).
+// Same contract as ctc.cu behind dae_ctc_lattice / dae_ctc_grad (torch.nn.CTCLoss semantics; call sites
+// lcasr/lib.py:492,570-579, AWMC :324-331).
 //
 // The per-frame chain needs T dependent steps on two SMs.  The recursion is linear in the (log-sum, +)
-// semiring, so it is cut into blocks of K frames and spread over the whole GPU in three launches:
-//   1. ctc_xfer_kernel      every (block, source state) in parallel: the K-frame transfer band
-//                           X_b[d][s] = log2 sum over paths that start in state s just before the block
-//                           and end in state s+d on its last frame (d <= 2K).  One thread per source, the
-//                           band lives in registers, no synchronisation.
-//   2. ctc_boundary_kernel  the only sequential part, T/K steps: boundary vectors
-//                           alpha_end(b)[s'] = LSE_d X_b[d][s'-d] + alpha_end(b-1)[s'-d]   and, with the same
-//                           bands read the other way, betahat_start(b)[s] = LSE_d X_b[d][s] + betahat_start(b+1)[s+d].
-//                           States are split into 64-state regions, one CTA each; a region only needs the last
-//                           2K values of the region below it, handed over through tagged 8-byte words in global
-//                           memory (tag in the data, no fences), so regions run as a skewed pipeline.
-//   3. ctc_fill_kernel      every (block, direction) in parallel: K ordinary lattice steps from the block's
-//                           boundary vector, written in the scratch layout ctc_grad_kernel reads.
+// semiring, so it is cut into blocks of K frames and spread over the whole GPU:
+//   dae_ctc_lattice
+//   1. ctc_xfer_kernel        every (block, source state) in parallel: the K-frame transfer band
+//                             X_b[s][d] = log2 sum over paths that start in state s just before the block and
+//                             end in state s+d on its last frame (d <= 2K).  One thread per source, the band
+//                             lives in registers, no synchronisation.  Also: label grouping for the gradient,
+//                             zeroing of the scan's hand-over words.
+//   2. ctc_boundary_kernel    the only sequential part, T/K steps: boundary vectors
+//                             alpha_end(b)[s'] = LSE_d X_b[s'-d][d] + alpha_end(b-1)[s'-d]   and, with the same
+//                             bands read the other way, betahat_start(b)[s] = LSE_d X_b[s][d] + betahat_start(b+1)[s+d].
+//                             States are split into 64-state regions, one CTA each; a region only needs the
+//                             last 2K values of the region below it, handed over as tagged 8-byte words (tag in
+//                             the data, no fences) through the receiver's shared memory inside a thread-block
+//                             cluster and through global memory across clusters: a skewed pipeline of regions.
+//                             Leaves the log-likelihood.
+//   dae_ctc_grad
+//   3. ctc_block_grad_kernel  every block in parallel: its K alpha rows and K beta rows are rebuilt in shared
+//                             memory from the boundary vectors and turned into the K gradient rows at once.
+//      (ctc_fill_kernel + ctc_grad_kernel do the same through the scratch buffer when a block's rows do not
+//      fit in shared memory.)
 // Values are log2 units with the finite dead-state sentinel of ctc_shared.cuh; every region / row carries an
 // fp64 offset so stored fp32 values stay O(1).
 #include <cooperative_groups.h>

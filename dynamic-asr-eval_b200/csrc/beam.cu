@@ -367,19 +367,14 @@ beam_search_kernel(BeamParams P) {
     if (tid == 0) S.n_unflagged = 0;
     __syncthreads();
     BeamRec* nxt = S.next_beams;
-    // survivor scores, compacted next to their creation indices (c_score is free after P4): the ranking loop
-    // then reads two broadcast words per comparison instead of chasing sv[l] -> c_final[.]
-    for (int j = tid; j < nsv; j += kBeamThreads) S.c_score[j] = S.c_final[S.sv[j]];
-    __syncthreads();
     // rank by (score desc, creation index asc); rank < beam_width survives at position rank
     for (int j = tid; j < nsv; j += kBeamThreads) {
       const int c = S.sv[j];
-      const float f = S.c_score[j];
+      const float f = S.c_final[c];
       int rank = 0;
-#pragma unroll 4
       for (int l = 0; l < nsv; ++l) {
         const int c2 = S.sv[l];
-        const float f2 = S.c_score[l];
+        const float f2 = S.c_final[c2];
         rank += (f2 > f) || (f2 == f && c2 < c);
       }
       if (rank < P.beam_width) {

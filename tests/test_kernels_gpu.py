@@ -266,6 +266,49 @@ def test_ctc_large_magnitude_precision(cuda, ctc_path):
     assert err < err_torch
 
 
+def test_ctc_long_label_sequence_two_pairs_per_thread(cuda, ctc_path):
+    """Lmax ~ 1000 labels: two state pairs per thread in the chain kernel; on the blocked path 32 scan regions
+    (four clusters) and the unfused fill + row-gradient fallback (a block's rows no longer fit in shared memory)."""
+    from dae.ctc import CTCLoss
+    T, N, C, L = 2100, 1, 48, 1000
+    g = torch.Generator().manual_seed(7)
+    blank = C - 1
+    tg = torch.randint(0, blank, (N, L), generator=g)
+    # posteriors loosely aligned with the labels (two frames per label), so the alignment is not adversarial
+    lp = torch.randn(T, N, C, generator=g)
+    idx = torch.arange(T).clamp_max(2 * L - 1) // 2
+    lp[torch.arange(T), 0, tg[0, idx]] += 4.0
+    lp = lp.log_softmax(-1)
+    x = lp.to(cuda).requires_grad_()
+    loss = CTCLoss(blank=blank, reduction="sum")(x, tg.to(cuda), [T], [L])
+    (loss / T).backward()
+    nll, grad = ctc_oracle.ctc_loss_grad(lp.double().numpy(), tg.numpy(), [T], [L], blank, gout=1.0 / T)
+    assert abs(loss.item() - nll[0]) <= 1e-5 * abs(nll[0])
+    _assert_ctc_grad_close(x.grad.cpu().numpy(), grad, lp.double().numpy(), 1.0 / T)
+
+
+def test_ctc_empty_inputs_and_targets(cuda, ctc_path):
+    """input_length 0 (loss 0 for the empty target, inf otherwise), target_length 0, and a normal sample in
+    one ragged batch: losses equal torch's, gradient rows of absent frames are zero."""
+    from dae.ctc import ctc_loss
+    T, N, C = 96, 4, 9
+    g = torch.Generator().manual_seed(11)
+    lp = torch.randn(T, N, C, generator=g).log_softmax(-1)
+    tg = torch.randint(0, C - 1, (N, 5), generator=g)
+    il = torch.tensor([0, 0, T, 70])
+    tl = torch.tensor([0, 3, 0, 5])
+    x = lp.to(cuda).requires_grad_()
+    nll = ctc_loss(x, tg.to(cuda), il, tl, blank=C - 1, reduction="none")
+    ref = torch.nn.functional.ctc_loss(lp, tg, il, tl, blank=C - 1, reduction="none")
+    assert nll[0].item() == 0.0 and torch.isinf(nll[1]) and nll[1] > 0
+    torch.testing.assert_close(nll[2:].cpu(), ref[2:], rtol=1e-5, atol=1e-5)
+    nll[2:].sum().backward()
+    got = x.grad.cpu()
+    _, grad = ctc_oracle.ctc_loss_grad(lp[:, 2:].double().numpy(), tg[2:].numpy(), il[2:].numpy(), tl[2:].numpy(), C - 1)
+    _assert_ctc_grad_close(got[:, 2:].numpy(), grad, lp[:, 2:].double().numpy(), 1.0)
+    assert torch.all(got[:, 0] == 0) and torch.all(got[70:, 3] == 0)
+
+
 # ---------------------------------------------------------------- stitch
 def test_stitch_matches_oracle(cuda):
     import dae._C as C_

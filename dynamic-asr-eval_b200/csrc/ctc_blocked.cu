@@ -202,6 +202,7 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
   __shared__ float oshift[2];                           // per step: shift of own values into the new frame
   __shared__ double Fd[2];                              // per step: the new frame itself
   __shared__ uint64_t full[kBndStages];
+  __shared__ __align__(8) int2 hstage[4][kHaloWords];   // cluster-boundary regions: hand-over words staged by cp.async
   const int g = blockIdx.x, dir = blockIdx.y, n = blockIdx.z, N = gridDim.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // Hand-over inside a thread-block cluster goes through the receiver's shared memory (DSMEM): the region below
@@ -321,31 +322,64 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
     const int2* hp = up_local ? (mbox + kHaloWords + lane)
                               : (halo0 + ((size_t)(dir ? (nb - 1) : 1) * G + (g > 0 ? g - 1 : 0)) * kHaloWords + lane);
     const bool polls = g > 0 && lane < kHaloWords;
-    // Words are requested two steps before they are consumed (one L2 round trip is longer than a step); the
-    // region below runs ahead by that much once the pipeline has filled.
-    int2 wa = make_int2(0, 0), wb = make_int2(0, 0);       // requests for the current and the next step
-    if (polls) {
-      wa = ld_tagged(hp);
-      if (nb > 1) wb = ld_tagged(hp + pstep);
+    if (up_local || g == 0) {
+      // -- mailbox in this CTA's shared memory (written by the region below through DSMEM): polling is cheap
+      __syncthreads();                           // "start"
+      for (int st = 0; st < nb; ++st) {
+        if (g > 0) {
+          int2 w = make_int2(0, 0);
+          if (polls) {
+            do { w = ld_tagged(hp); } while (w.y != st + 1);
+          }
+          const int lo = __shfl_sync(0xffffffffu, w.x, H), hi = __shfl_sync(0xffffffffu, w.x, H + 1);
+          const float hv = (lane < H) ? __int_as_float(w.x) : kDead;
+          if (lane < H) buf[(st + 1) & 1][lane] = hv;
+          const int hm = __reduce_max_sync(0xffffffffu, f2ord(hv));
+          if (lane == 0) {
+            hoff[(st + 1) & 1] = __hiloint2double(hi, lo);
+            hmaxs[(st + 1) & 1] = hm;
+          }
+          hp += pstep;
+        }
+        __syncthreads();                         // end of step st
+      }
+      return;
     }
+    // -- mailbox in global memory (cluster boundary).  An L2 round trip is longer than a step, and a load in
+    // flight is waited for at the step barrier, so the words are fetched with cp.async into a small staging
+    // ring kAhead steps before they are consumed (asynchronous copies are tracked by their own groups, not by
+    // the barrier), and the region starts kLead steps late so that those requests always find their words.
+    constexpr int kAhead = 3, kLead = 6;
+    {
+      const int v = nb < kLead ? nb : kLead;
+      const int2* late = hp + (int64_t)(v - 1) * pstep;
+      if (polls) while (ld_tagged(late).y != v) { }
+      __syncwarp();
+    }
+    auto request = [&](int v) {                  // stage the words of vector v (1-based) into slot v & 3
+      if (v <= nb && polls)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(&hstage[v & 3][lane])),
+                     "l"(hp + (int64_t)(v - 1) * pstep) : "memory");
+      cp_async_commit();
+    };
+    for (int v = 1; v <= kAhead; ++v) request(v);
     __syncthreads();                             // "start"
     for (int st = 0; st < nb; ++st) {
-      if (g > 0) {
-        int2 w = wa;
-        wa = wb;
-        if (polls) {
-          if (st + 2 < nb) wb = ld_tagged(hp + 2 * pstep);
-          while (w.y != st + 1) w = ld_tagged(hp);
-        }
-        const int lo = __shfl_sync(0xffffffffu, w.x, H), hi = __shfl_sync(0xffffffffu, w.x, H + 1);
-        const float hv = (lane < H) ? __int_as_float(w.x) : kDead;
-        if (lane < H) buf[(st + 1) & 1][lane] = hv;
-        const int hm = __reduce_max_sync(0xffffffffu, f2ord(hv));
-        if (lane == 0) {
-          hoff[(st + 1) & 1] = __hiloint2double(hi, lo);
-          hmaxs[(st + 1) & 1] = hm;
-        }
-        hp += pstep;
+      request(st + 1 + kAhead);                  // its slot held vector st+1-... consumed a step ago
+      cp_async_wait<kAhead>();                   // vector st+1 has landed
+      int2 w = make_int2(0, 0);
+      if (polls) {
+        w = ld_tagged(&hstage[(st + 1) & 3][lane]);
+        const int2* direct = hp + (int64_t)st * pstep;
+        while (w.y != st + 1) w = ld_tagged(direct);     // not published yet when requested: poll directly
+      }
+      const int lo = __shfl_sync(0xffffffffu, w.x, H), hi = __shfl_sync(0xffffffffu, w.x, H + 1);
+      const float hv = (lane < H) ? __int_as_float(w.x) : kDead;
+      if (lane < H) buf[(st + 1) & 1][lane] = hv;
+      const int hm = __reduce_max_sync(0xffffffffu, f2ord(hv));
+      if (lane == 0) {
+        hoff[(st + 1) & 1] = __hiloint2double(hi, lo);
+        hmaxs[(st + 1) & 1] = hm;
       }
       __syncthreads();                           // end of step st
     }

@@ -134,6 +134,12 @@ ctc_xfer_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, con
     for (int k = 0; k < K; ++k) es[k][j] = (k < kb && s < S) ? base[k * sT + cls] * kLog2e : kDead;
   }
   __syncthreads();
+  // the gradient pass reads the emissions of its frames from here (coalesced, no label indirection)
+  if (s0 + tid < sc.Sq) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (k < kb) sc.emis[((size_t)n * sc.nblk * K + (size_t)(t0 + k)) * sc.Sq + s0 + tid] = es[k][tid];
+  }
   // warps 0-3 own the even sources of the tile, warps 4-7 the odd ones
   const int par = tid >> 7;
   const int jl = 2 * (tid & 127) + par;
@@ -851,12 +857,12 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
     const int p = tid + j * NTc;
     p2[j] = 2 * p;
     lead_q[j] = (p < L) ? (sc.leader[(int64_t)n * Lp + p] != 0) : false;
-    const int cls = (p < L) ? (int)tgt[n * tgt_stride + p] : blank;
+    const float* em = sc.emis + ((size_t)n * sc.nblk * K + (size_t)t0) * sc.Sq + (2 * p + 1);   // written by ctc_xfer_kernel
 #pragma unroll
     for (int k = 0; k < K; ++k)
-      xla[j][k] = (k < kb && p < L) ? base[(int64_t)(t0 + k) * sT + cls] * kLog2e : kDead;
+      xla[j][k] = (k < kb && p < L) ? __ldcg(em + (size_t)k * sc.Sq) : kDead;
   }
-  const float xb_mine = (tid < kb) ? base[(int64_t)(t0 + tid) * sT + blank] * kLog2e : kDead;
+  const float xb_mine = (tid < kb) ? __ldcg(sc.emis + ((size_t)n * sc.nblk * K + (size_t)(t0 + tid)) * sc.Sq) : kDead;
   if (dense_first) dense();
   for (int k = tid; k < L; k += NTc) {
     lab[k] = (int)tgt[n * tgt_stride + k];

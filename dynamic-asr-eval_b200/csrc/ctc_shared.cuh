@@ -25,6 +25,7 @@ struct CtcScratch {           // carved out of the caller's scratch buffer
   float* bound;               // [2][N][nblk+1][Sq]   lattice vectors at block boundaries, centred per 128-state region
   double* boff;               // [2][N][nblk+1][G]    offset of each 128-state region of a boundary vector
   int2* halo;                 // [2][N][nblk+1][G][kHaloWords]  tagged {bits, tag} words handed to the next region
+  float* emis;                // [N][nblk*K][Sq]  emission (log2 units) of every lattice state at every frame
   int nblk, G, Sq;
 };
 
@@ -79,7 +80,7 @@ static inline size_t ctc_carve(CtcScratch& s, void* base, int T, int N, int Lmax
   s.off_a = (double*)(p + off); off += offs;
   s.off_b = (double*)(p + off); off += offs;
   s.ll2 = (double*)(p + off); off += align_up((size_t)4 * N * sizeof(double), 256);
-  s.xfer = nullptr; s.bound = nullptr; s.boff = nullptr; s.halo = nullptr;
+  s.xfer = nullptr; s.bound = nullptr; s.boff = nullptr; s.halo = nullptr; s.emis = nullptr;
   s.nblk = 0; s.G = 0; s.Sq = 0;
   if (blocked_eligible(T, N, Lmax)) {
     s.nblk = (T + kBlkK - 1) / kBlkK;
@@ -89,6 +90,7 @@ static inline size_t ctc_carve(CtcScratch& s, void* base, int T, int N, int Lmax
     s.bound = (float*)(p + off); off += align_up((size_t)2 * N * (s.nblk + 1) * s.Sq * sizeof(float), 256);
     s.boff = (double*)(p + off); off += align_up((size_t)2 * N * (s.nblk + 1) * s.G * sizeof(double), 256);
     s.halo = (int2*)(p + off); off += align_up((size_t)2 * N * (s.nblk + 1) * s.G * kHaloWords * sizeof(int2), 256);
+    s.emis = (float*)(p + off); off += align_up((size_t)N * s.nblk * kBlkK * s.Sq * sizeof(float), 256);
   }
   return off;
 }

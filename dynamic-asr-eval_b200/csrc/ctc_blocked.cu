@@ -808,27 +808,36 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
 
   // ---- 0. dense part (zeros for the padding frames of a short sample): all K rows of a column chunk are loaded
   // before any is stored, so a thread keeps K independent 128-bit loads in flight.
-  auto dense = [&]() {
-    if (vec) {
-      constexpr int KH = K / 2;                    // two half batches: K/2 independent 128-bit loads in flight
-      for (int i = tid; i < (C >> 2); i += NTc) {
+  // `occ` (shared memory, [K/2][Cq]) holds, per row of the half batch, the occupancy of every class: then the rows
+  // leave complete, as 128-bit stores only; without it the caller overwrites the few classes that occur later.
+  constexpr int KH = K / 2;                        // half batches: K/2 independent 128-bit loads in flight
+  const int Cq = (C + 3) & ~3;
+  auto dense_half = [&](int hb, const float* occ) {
+    for (int i = tid; i < (C >> 2); i += NTc) {
+      float4 v4[KH];
 #pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-          float4 v4[KH];
+      for (int k = 0; k < KH; ++k)
+        if (hb * KH + k < kb) v4[k] = __ldcs(reinterpret_cast<const float4*>(base + (int64_t)(t0 + hb * KH + k) * sT) + i);
 #pragma unroll
-          for (int k = 0; k < KH; ++k)
-            if (hb * KH + k < kb) v4[k] = __ldcs(reinterpret_cast<const float4*>(base + (int64_t)(t0 + hb * KH + k) * sT) + i);
-#pragma unroll
-          for (int k = 0; k < KH; ++k) {
-            const int kk = hb * KH + k;
-            if (kk < krows) {
-              float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (kk < kb) o4 = make_float4(__expf(v4[k].x) * g, __expf(v4[k].y) * g, __expf(v4[k].z) * g, __expf(v4[k].w) * g);
-              __stcs(reinterpret_cast<float4*>(grad + ((int64_t)(t0 + kk) * N + n) * C) + i, o4);
-            }
+      for (int k = 0; k < KH; ++k) {
+        const int kk = hb * KH + k;
+        if (kk < krows) {
+          float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kk < kb) {
+            float4 oc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (occ) oc = *reinterpret_cast<const float4*>(occ + k * Cq + 4 * i);
+            o4 = make_float4((__expf(v4[k].x) - oc.x) * g, (__expf(v4[k].y) - oc.y) * g, (__expf(v4[k].z) - oc.z) * g,
+                             (__expf(v4[k].w) - oc.w) * g);
           }
+          __stcs(reinterpret_cast<float4*>(grad + ((int64_t)(t0 + kk) * N + n) * C) + i, o4);
         }
       }
+    }
+  };
+  auto dense = [&]() {
+    if (vec) {
+      dense_half(0, nullptr);
+      dense_half(1, nullptr);
     } else {
       for (int k = 0; k < krows; ++k) {
         float* orow = grad + ((int64_t)(t0 + k) * N + n) * C;
@@ -837,9 +846,12 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
       }
     }
   };
+  // With room for the occupancy table (the alpha/beta rows are dead by then) the rows are written once, at the
+  // end.  Otherwise:
   // half of the grid streams first and runs its chains later, the other half the other way round, so the two
   // CTAs that share an SM overlap memory traffic with the latency-bound chains
-  const bool dense_first = (int)blockIdx.x * 2 < (int)gridDim.x || kb == 0;
+  const bool table = vec && (size_t)KH * Cq <= (size_t)2 * K * lay.row_stride;
+  const bool dense_first = !table && ((int)blockIdx.x * 2 < (int)gridDim.x || kb == 0);
   if (kb == 0) {
     dense();
     return;
@@ -1023,7 +1035,7 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
     }
   }
 
-  if (!dense_first) dense();
+  if (!dense_first && !table) dense();
   __syncthreads();                               // dense stores of every thread precede the sparse overwrite
 
   // ---- 2. occupancies and the sparse correction (gam: label emissions are replaced by label occupancies)
@@ -1060,21 +1072,54 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
     }
   }
   __syncthreads();
+  // per class occupancy: the first occurrence of a class walks its list (members in label order)
+  float acc[P][K];
 #pragma unroll
   for (int j = 0; j < P; ++j) {
     const int q = p2[j] >> 1;
-    if (lead_q[j]) {
-      float acc[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc[k] = 0.0f;
+    for (int k = 0; k < K; ++k) acc[j][k] = 0.0f;
+    if (lead_q[j]) {
       for (int m = q; m >= 0; m = nxt[m]) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] += gam[k * Lp + m];
+        for (int k = 0; k < K; ++k) acc[j][k] += gam[k * Lp + m];
       }
-      const int c = lab[q];
+    }
+  }
+  if (table) {
+    // alpha/beta rows are dead: their space becomes the occupancy table of a half batch of rows
+    float* occ = reinterpret_cast<float*>(smem_raw + lay.rowsA);
+    __syncthreads();                             // every thread is done with the rows
+    for (int i = tid; i < KH * Cq; i += NTc) occ[i] = 0.0f;
+    __syncthreads();
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        if (lead_q[j]) {
+          const int c = lab[p2[j] >> 1];
+#pragma unroll
+          for (int k = 0; k < KH; ++k) occ[k * Cq + c] = acc[j][hb * KH + k];
+        }
+      }
+      if (tid < KH) {
+        float sacc = 0.0f;
+        for (int w = 0; w < nw; ++w) sacc += bsum_s[w * K + hb * KH + tid];
+        occ[tid * Cq + blank] = sacc;
+      }
+      __syncthreads();
+      dense_half(hb, occ);
+      __syncthreads();                           // the next half batch overwrites the same table entries
+    }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    if (lead_q[j]) {
+      const int c = lab[p2[j] >> 1];
 #pragma unroll
       for (int k = 0; k < K; ++k)
-        if (k < kb) grad[((int64_t)(t0 + k) * N + n) * C + c] = (fast_ex2(xla[j][k]) - acc[k]) * g;
+        if (k < kb) grad[((int64_t)(t0 + k) * N + n) * C + c] = (fast_ex2(xla[j][k]) - acc[j][k]) * g;
     }
   }
   if (tid < kb) {

@@ -859,7 +859,6 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
 
   // ---- 1a. labels, list links, emissions of the block's frames at every label state.  All global loads of the
   // prologue are issued before the dense stream starts, so their latency hides behind it.
-  const int t1 = t0 + kb - 1;
   const double ll2 = sc.ll2[n];
   int p2[P];
   bool lead_q[P];

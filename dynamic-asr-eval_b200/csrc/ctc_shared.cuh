@@ -105,14 +105,6 @@ __device__ __forceinline__ float fast_lg2(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// log2(2^a + 2^b + 2^c) with 3 MUFU ops: the largest term contributes exactly 1.
-// -inf inputs allowed; all -inf -> -inf.
-__device__ __forceinline__ float lse3_2(float a, float b, float c) {
-  const float lo = fminf(a, b), hi = fmaxf(a, b);
-  const float m = fmaxf(hi, c), mid = fminf(hi, c);
-  if (m == -CUDART_INF_F) return m;
-  return m + fast_lg2(1.0f + fast_ex2(mid - m) + fast_ex2(lo - m));
-}
 // Order-preserving float <-> int map so a warp max can use redux.sync / smem atomicMax.
 __device__ __forceinline__ int f2ord(float f) {
   const int i = __float_as_int(f);
@@ -120,12 +112,6 @@ __device__ __forceinline__ int f2ord(float f) {
 }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
-// log2(2^a + 2^b), 2 MUFU ops.
-__device__ __forceinline__ float lse2_2(float a, float b) {
-  const float m = fmaxf(a, b), lo = fminf(a, b);
-  if (m == -CUDART_INF_F) return m;
-  return m + fast_lg2(1.0f + fast_ex2(lo - m));
-}
 // Branch-free variants for the lattice: dead states hold the finite sentinel kDead instead of -inf
 // (kDead + anything finite == kDead in fp32, and kDead - kDead == 0, so no NaN can appear).
 constexpr float kDead = -1.0e30f;

@@ -223,6 +223,9 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
     for (int k = tid; k < (sc.nblk + 1) * kHaloWords; k += blockDim.x) mbox[k] = make_int2(0, 0);
     cluster.sync();
   }
+  // Launched with programmatic stream serialization: everything above overlaps the band kernel's tail; its
+  // results (bands, zeroed hand-over words, label groups) are visible from here on.
+  cudaGridDependencySynchronize();
   if (g >= sc.G) return;                                // grid padded to whole clusters
   const bool up_local = CL > 1 && crank > 0 && g > 0;
   const bool down_local = CL > 1 && crank + 1 < CL && g + 1 < sc.G;
@@ -1186,13 +1189,15 @@ int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, i
     cfg.blockDim = dim3(kBndThreads);
     cfg.dynamicSmemBytes = cl > 1 ? mbox_bytes : 0;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cl;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // prologue overlaps the band kernel
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     if (cfg.dynamicSmemBytes > 24 * 1024)
       DAE_CUDA(cudaFuncSetAttribute(ctc_boundary_kernel<kBlkK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)cfg.dynamicSmemBytes));

@@ -165,3 +165,19 @@ def test_cutout_oracle_matches_reference(mode):
     out = cutout_oracle.cutout(spec, rects, mode)
     np.testing.assert_allclose(out, gold, rtol=0, atol=1e-6)        # means: torch fp32 sum vs numpy pairwise
     assert (out != spec).any()
+
+
+@pytest.mark.parametrize("T,C,L,K", [(37, 11, 9, 8), (16, 6, 7, 8), (8, 5, 0, 8), (5, 5, 2, 8), (20, 4, 9, 4), (19, 7, 5, 16)])
+def test_blocked_ctc_decomposition_equals_per_frame_recursion(T, C, L, K):
+    """The time-blocked factorisation the GPU path uses (transfer bands, boundary scan in both directions, block
+    fill) is the same function as the per-frame recursion: loss and gradient agree with ctc_oracle in fp64."""
+    from oracle import ctc_blocked_oracle, ctc_oracle
+    rng = np.random.default_rng(T * 100 + L)
+    lp = np.log(rng.dirichlet(np.ones(C), size=T))
+    labels = list(rng.integers(0, C - 1, size=L))
+    if L > 3:
+        labels[2] = labels[1]                                  # a repeated label: no skip transition there
+    nll_b, grad_b = ctc_blocked_oracle.ctc_loss_grad_blocked(lp, labels, C - 1, K)
+    nll, grad = ctc_oracle.ctc_loss_grad(lp[:, None, :], [labels], [T], [L], C - 1)
+    assert abs(nll_b - nll[0]) <= 1e-10 * max(1.0, abs(nll[0]))
+    np.testing.assert_allclose(grad_b, grad[:, 0], rtol=0, atol=1e-10)

@@ -479,7 +479,7 @@ extern "C" int dae_beam_search(const float* lp, const int32_t* seg_offsets, int 
   P.out_n = out_n;
   const int smem = (int)(((sizeof(BeamSmem) + 15) / 16) * 16 + 2 * (size_t)((C + 3) & ~3) * sizeof(float));
   if (smem > 220 * 1024) return DAE_E_TOOBIG;
-  DAE_CUDA(cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  DAE_CUDA(ensure_dyn_smem(beam_search_kernel, smem));
   beam_search_kernel<<<n_seg, kBeamThreads, smem, (cudaStream_t)stream>>>(P);
   DAE_LAUNCH_OK();
   return 0;

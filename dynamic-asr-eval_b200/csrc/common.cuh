@@ -59,6 +59,15 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Raise a kernel's dynamic shared-memory limit, once per (kernel, device, size): the driver call costs a few
+// microseconds of host time, which shows when the GPU is waiting for the launch.  (Not thread-safe beyond benign
+// double-setting: the table only ever grows and a lost update costs one more driver call.)
+cudaError_t ensure_dyn_smem_impl(const void* kern, int bytes);
+template <typename Kern>
+inline cudaError_t ensure_dyn_smem(Kern kern, int bytes) {
+  return ensure_dyn_smem_impl(reinterpret_cast<const void*>(kern), bytes);
+}
+
 __host__ __device__ __forceinline__ bool aligned16(const void* p) {
   return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
 }

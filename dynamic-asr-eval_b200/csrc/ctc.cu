@@ -404,7 +404,7 @@ template <int P>
 static int launch_lattice(int NT, const LatSmem& lay, int vec, cudaStream_t st, int N, const float* lp, int64_t sT,
                           int64_t sN, int T, int C, const int64_t* tgt, int64_t tgt_stride, int Lmax,
                           const int64_t* in_len, const int64_t* tgt_len, int blank, float* nll, const CtcScratch& sc) {
-  DAE_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+  DAE_CUDA(ensure_dyn_smem(ctc_lattice_kernel<P>, lay.total));
   ctc_lattice_kernel<P><<<dim3(2, N), NT, lay.total, st>>>(lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len,
                                                           blank, nll, sc, lay, vec);
   DAE_LAUNCH_OK();
@@ -476,7 +476,7 @@ extern "C" int dae_ctc_grad(const float* lp, int64_t sT, int64_t sN, int T, int 
   const size_t smem = (size_t)((C + 3) & ~3) * 4 + (size_t)sc.Lp * 4;
   if (smem > 200 * 1024) return DAE_E_TOOBIG;
   if (smem > 48 * 1024)
-    DAE_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAE_CUDA(ensure_dyn_smem(ctc_grad_kernel, (int)smem));
   const int vec = aligned16(lp) && aligned16(grad) && (C % 4 == 0) && (sT % 4 == 0) && (sN % 4 == 0);
   int work = (C / 4 > 2 * Lmax + 1) ? C / 4 : 2 * Lmax + 1;
   int NT = ((work + 31) / 32) * 32;

@@ -726,7 +726,7 @@ static int launch_fill(int NTc, cudaStream_t st, int N, const float* lp, int64_t
   if (lay.total > 200 * 1024) return DAE_E_TOOBIG;
   auto kern = ctc_fill_kernel<P, kBlkK, MAXT, MINB>;
   if (lay.total > 48 * 1024)
-    DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+    DAE_CUDA(ensure_dyn_smem(kern, lay.total));
   kern<<<dim3(sc.nblk, 2, N), NTc, lay.total, st>>>(lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, sc,
                                                     lay);
   DAE_LAUNCH_OK();
@@ -1137,7 +1137,7 @@ static int launch_block_grad(int NTc, cudaStream_t st, int N, const float* lp, i
                              const int64_t* tgt_len, int blank, const float* gout, int64_t gout_stride, float* grad,
                              const CtcScratch& sc, const BgSmem& lay, int vec) {
   auto kern = ctc_block_grad_kernel<P, kBlkK, MAXT, MINB>;
-  DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+  DAE_CUDA(ensure_dyn_smem(kern, lay.total));
   kern<<<dim3(sc.nblk, N), NTc, lay.total, st>>>(lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, gout,
                                                  gout_stride, grad, sc, lay, vec);
   DAE_LAUNCH_OK();
@@ -1199,8 +1199,7 @@ int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, i
     cfg.attrs = attr;
     cfg.numAttrs = 2;
     if (cfg.dynamicSmemBytes > 24 * 1024)
-      DAE_CUDA(cudaFuncSetAttribute(ctc_boundary_kernel<kBlkK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)cfg.dynamicSmemBytes));
+      DAE_CUDA(ensure_dyn_smem(ctc_boundary_kernel<kBlkK>, (int)cfg.dynamicSmemBytes));
     DAE_CUDA(cudaLaunchKernelEx(&cfg, ctc_boundary_kernel<kBlkK>, T, Lmax, in_len, tgt_len, nll, sc));
     DAE_LAUNCH_OK();
   }

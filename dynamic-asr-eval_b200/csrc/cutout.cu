@@ -91,7 +91,7 @@ extern "C" int dae_cutout(float* x, int64_t sF, int F, int T, const int32_t* rec
   const int grid = (int)(want < (int64_t)kNumSMs * 8 ? want : (int64_t)kNumSMs * 8);
   const size_t smem = (size_t)n_rect * sizeof(int4);
   if (smem > 48 * 1024)
-    DAE_CUDA(cudaFuncSetAttribute(cutout_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAE_CUDA(ensure_dyn_smem(cutout_apply_kernel, (int)smem));
   cutout_apply_kernel<<<grid, 256, smem, st>>>(x, sF, F, T, d_rects, n_rect, mode, d_means);
   DAE_LAUNCH_OK();
   return 0;

@@ -21,3 +21,28 @@ extern "C" const char* dae_error_string(int code) {
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   return "dae: unknown error";
 }
+
+namespace dae {
+cudaError_t ensure_dyn_smem_impl(const void* kern, int bytes) {
+  struct Entry { const void* kern; int dev; int bytes; };
+  static Entry table[128];
+  static int used = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const int n = used;
+  for (int i = 0; i < n; ++i)
+    if (table[i].kern == kern && table[i].dev == dev) {
+      if (table[i].bytes >= bytes) return cudaSuccess;
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e == cudaSuccess) table[i].bytes = bytes;
+      return e;
+    }
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && n < 128) {
+    table[n] = Entry{kern, dev, bytes};
+    used = n + 1;
+  }
+  return e;
+}
+}  // namespace dae

@@ -358,7 +358,7 @@ static int softdtw_launch(const float* D, float* R, float* E, float* out, const 
   const int smem = smem_per_warp * warps;
   const bool prune = bandwidth > 0.0f;
   auto kern = prune ? softdtw_wave_kernel<BWD, true> : softdtw_wave_kernel<BWD, false>;
-  DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  DAE_CUDA(ensure_dyn_smem(kern, smem));
   const int agents = B * P.nbands;
   int grid = (agents + warps - 1) / warps;
   if (grid > kNumSMs) grid = kNumSMs;                     // persistent: one CTA per SM, tickets do the rest

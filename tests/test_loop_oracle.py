@@ -70,3 +70,31 @@ def test_oracle_awmc_matches_reference_golden():
     assert sum(got) <= sum(gold_lens)
     np.testing.assert_allclose(np.exp(logits), np.exp(GOLD["logits_awmc"]), rtol=2e-4, atol=1e-7)
     assert all(torch.equal(a, b) for a, b in zip(before, model.parameters()))
+
+
+def test_chunking_and_positions_properties_random_sizes():
+    """Host index arithmetic of the product (dae.lib.prepare_chunks, dae.stitch.window_positions) against the
+    oracle restatement of lcasr/lib.py:128-145,586-621 over random recording lengths, windows and overlaps:
+    same windows, same output positions; windows tile the recording with the stride seq_len - overlap."""
+    import random
+
+    import torch
+
+    from dae.lib import prepare_chunks
+    from dae.stitch import window_positions
+    from oracle import stitch_oracle
+    rnd = random.Random(0)
+    for _ in range(200):
+        seq = rnd.choice([64, 512, 2048, 16384])
+        overlap = rnd.choice([0, seq // 8, seq // 2, seq - seq // 8])
+        spec_n = rnd.randint(1, 6 * seq)
+        spec = torch.zeros(1, 2, spec_n)
+        chunks, starts = prepare_chunks(spec, seq, overlap)
+        ref = stitch_oracle.prepare_chunks(spec_n, seq, overlap)
+        assert list(starts) == [s for s, _ in ref]
+        assert [int(chunks[s].shape[-1]) for s in starts] == [l for _, l in ref]
+        stride = seq - overlap
+        assert all(b - a == stride for a, b in zip(starts, starts[1:]))
+        u_lens = [l for _, l in ref]
+        ds = [max(1, l // 8) for l in u_lens]                      # x8 subsampling stand-in
+        assert window_positions(starts, u_lens, ds, overlap) == stitch_oracle.window_positions(starts, u_lens, ds, overlap)

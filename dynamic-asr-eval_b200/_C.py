@@ -31,6 +31,10 @@ _PROTOS = {
                                    c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dae_cutout_scratch_bytes": (c_size_t, [c_int]),
     "dae_cutout": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "dae_frame_shuffle": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dae_noise_scratch_bytes": (c_size_t, []),
+    "dae_add_noise": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, ctypes.c_float, c_void_p, c_size_t,
+                              c_void_p, c_void_p]),
     "dae_ctc_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dae_ctc_lattice": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
                                 c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -39,12 +43,14 @@ _PROTOS = {
                              c_void_p, c_size_t, c_void_p]),
     "dae_softdtw_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dae_softdtw_fwd": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p,
-                                c_void_p, c_size_t, c_void_p]),
-    "dae_softdtw_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, ctypes.c_float,
-                                ctypes.c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dae_softdtw_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                c_void_p]),
     "dae_beam_scratch_bytes": (c_size_t, [c_int, c_int]),
     "dae_ngram_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                  ctypes.c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dae_ngram_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                               ctypes.c_float, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dae_beam_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
                                 ctypes.c_float, ctypes.c_float, c_int, ctypes.c_float, ctypes.c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

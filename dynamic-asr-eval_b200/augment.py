@@ -152,3 +152,62 @@ def cutout(spec, seq_len, cutout_val="mean", num_rectangles=5, max_width=100, ma
                             scratch.data_ptr(), nbytes, _C.stream_ptr(x.device))
     _C.check(rc, "dae_cutout")
     return spec
+
+
+def draw_frame_shuffle(F, T, time_dimension=False, freq_dimension=False, generator=None):
+    """Permutations of lcasr/lib.py:81-84 from the HOST generator in the reference's order: randperm(T) if
+    time_dimension, then randperm(F) if freq_dimension.  -> (perm_t or None, perm_f or None), int64 CPU."""
+    pt = torch.randperm(T, generator=generator) if time_dimension else None
+    pf = torch.randperm(F, generator=generator) if freq_dimension else None
+    return pt, pf
+
+
+def frame_shuffle(spec, time_dimension=False, freq_dimension=False, perms=None):
+    """lcasr/lib.py:81-84 on the GPU: ``spec[:, :, randperm(T)]`` then ``spec[:, randperm(F), :]`` as one gather
+    kernel.  ``spec`` [B,F,T] fp32 CUDA; like the reference, ONE permutation per axis is shared by the batch.
+    ``perms`` = (perm_t, perm_f) overrides the draw (tests / replay)."""
+    if not (time_dimension or freq_dimension):
+        return spec
+    _C.require_cuda(spec, "spec")
+    if spec.dim() != 3 or spec.dtype != torch.float32:
+        raise _C.DaeError("frame_shuffle needs a [B,F,T] fp32 tensor")
+    B, F, T = spec.shape
+    pt, pf = perms if perms is not None else draw_frame_shuffle(F, T, time_dimension, freq_dimension)
+    dev = spec.device
+    dpt = pt.to(torch.int32).to(dev, non_blocking=True) if pt is not None else None
+    dpf = pf.to(torch.int32).to(dev, non_blocking=True) if pf is not None else None
+    out = torch.empty((B, F, T), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), prof.span("frame_shuffle", 2 * B * F * T * 4):
+        for b in range(B):
+            src = spec[b] if spec[b].stride(1) == 1 else spec[b].contiguous()
+            rc = _C.lib().dae_frame_shuffle(src.data_ptr(), src.stride(0), F, T, _C.ptr(dpt), _C.ptr(dpf),
+                                            out[b].data_ptr(), _C.stream_ptr(dev))
+            _C.check(rc, "dae_frame_shuffle")
+    return out
+
+
+def add_random_noise(spec, noise_factor, z=None):
+    """lcasr/lib.py:379-382 on the GPU, in place on ``spec`` ([B,F,T] or [F,T] fp32 CUDA):
+    ``spec + torch.normal(0, spec.std(), size) * noise_factor``.  The reference draws on the CPU from the global
+    generator; ``torch.normal(0, s, size)`` is bitwise ``torch.randn(size) * s`` with the same generator
+    consumption, so the standard-normal field ``z`` is drawn on the host (or passed in) and the std / scale /
+    add run in dae_add_noise."""
+    if noise_factor == 0:
+        return spec
+    _C.require_cuda(spec, "spec")
+    if spec.dtype != torch.float32 or not spec.is_contiguous():
+        raise _C.DaeError("add_random_noise needs a contiguous fp32 tensor")
+    if z is None:
+        z = torch.randn(spec.shape)
+    if not z.is_cuda:
+        prof.count_h2d(z)
+    zd = z.to(device=spec.device, dtype=torch.float32, non_blocking=True).contiguous()
+    rows, T = spec.numel() // spec.shape[-1], spec.shape[-1]
+    lib = _C.lib()
+    n = lib.dae_noise_scratch_bytes()
+    scratch = torch.empty(n, dtype=torch.uint8, device=spec.device)
+    with torch.cuda.device(spec.device), prof.span("add_noise", 3 * spec.numel() * 4):
+        rc = lib.dae_add_noise(spec.data_ptr(), T, rows, T, zd.data_ptr(), float(noise_factor), scratch.data_ptr(), n,
+                               None, _C.stream_ptr(spec.device))
+    _C.check(rc, "dae_add_noise")
+    return spec

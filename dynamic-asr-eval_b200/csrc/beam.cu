@@ -115,6 +115,21 @@ ngram_expand_kernel(DaeNgram lm, int n_ctx, float* __restrict__ row, int32_t* __
   }
 }
 
+// Rows for an explicit list of LM states (the LanguageModel duck type's per-beam next-token log-probs,
+// lcasr/ctc_beam_search.py:70-87): row[j*V + w] = log p(w | states[j]); same walk, bit-identical to the search.
+__global__ void __launch_bounds__(256)
+ngram_rows_kernel(DaeNgram lm, const int32_t* __restrict__ states, int n_states, float* __restrict__ row,
+                  int32_t* __restrict__ next) {
+  const size_t n = (size_t)n_states * lm.V;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i / lm.V), w = (int)(i - (size_t)j * lm.V);
+    int node = __ldg(states + j);
+    if (node < 0 || node >= lm.n_nodes) node = 0;
+    row[i] = lm_score_walk(lm, node, w);
+    if (next) next[i] = lm_next_state_walk(lm, node, w);
+  }
+}
+
 // ctc_beam_search.py:157-159 under torch/NumPy-2 semantics: fp32 difference, fp64 exp/log, fp32 add.
 __device__ __forceinline__ float sum_log_scores(float s1, float s2) {
   if (s1 >= s2) return __fadd_rn(s1, (float)log(1.0 + exp((double)__fsub_rn(s2, s1))));
@@ -498,6 +513,23 @@ extern "C" int dae_ngram_expand(const int32_t* lm_tok, const float* lm_logp, con
   size_t want = (n + 255) / 256;
   const int grid = (int)(want < (size_t)kNumSMs * 16 ? want : (size_t)kNumSMs * 16);
   ngram_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lm, n_ctx, row, next);
+  DAE_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int dae_ngram_rows(const int32_t* lm_tok, const float* lm_logp, const float* lm_bo, const int32_t* lm_fail,
+                              const int32_t* lm_cb, const int32_t* lm_depth, int lm_nodes, int lm_order, float lm_unk_lp,
+                              int vocab, const int32_t* states, int n_states, float* row, int32_t* next, void* stream) {
+  using namespace dae;
+  if (!lm_tok || !lm_logp || !lm_bo || !lm_fail || !lm_cb || !lm_depth || !row || !states || lm_nodes < 1 ||
+      lm_order < 1 || vocab < 1 || n_states < 0)
+    return DAE_E_BADARG;
+  if (n_states == 0) return 0;
+  DaeNgram lm{lm_tok, lm_logp, lm_bo, lm_fail, lm_cb, lm_depth, lm_nodes, lm_order, 0, lm_unk_lp, nullptr, nullptr, vocab};
+  const size_t n = (size_t)n_states * vocab;
+  size_t want = (n + 255) / 256;
+  const int grid = (int)(want < (size_t)kNumSMs * 16 ? want : (size_t)kNumSMs * 16);
+  ngram_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lm, states, n_states, row, next);
   DAE_LAUNCH_OK();
   return 0;
 }

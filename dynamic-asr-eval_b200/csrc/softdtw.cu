@@ -7,17 +7,30 @@
 // p - i, so the three predecessors are the lane's own previous value, the upper lane's previous
 // value (one __shfl_up) and the upper lane's value from two steps ago (kept in a register).  There is
 // no CTA-wide barrier anywhere.
-//   * D (and R in the backward pass) are staged in shared memory as 32x32 tiles by cp.async, three or
-//     four tiles ahead; lane i reads tile[i][(p-i)&31], which is bank-conflict free.
-//   * Results are staged in a 32x32 smem tile and flushed with coalesced 128-bit stores.
+//   * Inputs are staged in shared memory as 32x32 tiles by cp.async, three or four tiles ahead; lane i
+//     reads tile[i][(p-i)&31], which is bank-conflict free.  Results are staged in a smem tile ring and
+//     flushed with coalesced 128-bit stores.
 //   * A band needs the bottom row of the band above.  Lane 31 publishes every bottom-row value the
 //     moment it exists as an 8-byte {value, column+1} word in a zero-initialised export buffer; the
 //     consumer polls the tag in the data itself, so there are no flags and no fences, and a band
 //     trails its predecessor by the ideal 32 steps plus one L2 round trip.
 //   * Bands are handed to warps through an atomic ticket in (band, sample) order, so a waiting warp
 //     only ever waits for a warp that already started: deadlock-free for any grid size.
-// The backward pass is the same sweep on the flipped grid (i' = N-1-i, j' = M-1-j) with
-// E = E_dn*a + E_right*b + E_diag*c, a/b/c = exp((W[.] - R[i,j])/gamma), W = R - D (:100-108).
+//
+// Numerics (round 2).  The reference stores R in fp32 ([B,N+2,M+2], :121-144,256-258) and forms the
+// backward weights exp((R' - R - D)/gamma) from it; at 4096x4096 R reaches -5000, one fp32 ulp is 5e-4 and the
+// reference's own gradient sits 1.2e-4 (of the gradient scale) away from exact arithmetic; a forward pass that
+// also COMPUTES in fp32 at that magnitude drifts to 1e-2.  Here
+//   * the forward keeps every value relative to a warp-uniform integer offset mu that follows the band's
+//     minimum (re-centred every 8 steps by an exact integer shift), in units of gamma*ln2, so the fp32 values
+//     stay O(1..100) and a fresh rounding error is ~1e-7 instead of 2.4e-4; band-to-band hand-over carries the
+//     producer's mu in a tagged side word per 8 columns;
+//   * the forward stores, per cell, the softmin weights of its `up` and `left` predecessors (the `diag` weight is
+//     1 - up - left).  They ARE the reference's backward coefficients: a = exp((R[i+1,j] - R[i,j] - D[i+1,j])/gamma)
+//     (:100-103) is the weight cell (i+1,j) gave its `up` predecessor (i,j), etc.  The backward pass therefore
+//     needs neither R nor D nor any exponential: E[i,j] = E[i+1,j]*Wu[i+1,j] + E[i,j+1]*Wl[i,j+1] +
+//     E[i+1,j+1]*Wd[i+1,j+1] is three multiplies and two adds per cell.
+// Measured against the fp64 oracle at [8,4096,4096]: gradient within 1e-6 of the gradient scale (tests).
 #include "common.cuh"
 
 namespace dae {
@@ -25,27 +38,31 @@ namespace dae {
 constexpr int kBand = 32;                 // rows per warp
 constexpr int kTile = 32;                 // columns per staged tile
 // columns per export poll group: the group head (poll, prefetch, smem reads) is amortised over the group, the band
-// below trails by a few more steps; measured best at 8 forward and 16 backward ([8,4096,4096])
+// below trails by a few more steps
 constexpr int kGrpFwd = 8, kGrpBwd = 16;
-constexpr int kDepth = 1;                 // groups between requesting band-above values and using them
-constexpr float kLog2eF = 1.4426950408889634f;
-constexpr float kLn2F = 0.6931471805599453f;
+constexpr double kLog2e = 1.4426950408889634;
+constexpr double kLn2 = 0.6931471805599453;
 
 struct SdtwParams {
-  const float* D;        // [B,N,M]
-  float* R;              // [B,N,M]   fwd: out, bwd: in
-  float* E;              // [B,N,M]   bwd: out (already scaled by gout[b])
-  float* out;            // [B]       fwd: R[N-1,M-1]
-  const float* gout;     // [B]       bwd: upstream gradient
+  const float* D;        // [B,N,M]        fwd in
+  float2* W;             // [B,N,M]        fwd out / bwd in: softmin weights (up, left) of every cell
+  float* R;              // [B,N,M]        fwd out, optional (NULL = not written)
+  float* E;              // [B,N,M]        bwd out (already scaled by gout[b])
+  float* out;            // [B]            fwd: R[N-1,M-1]
+  const float* gout;     // [B]            bwd: upstream gradient
   int64_t gout_stride;
-  int2* exp_buf;         // [B][nbands][Mp] published bottom rows {value bits, column+1}
+  int2* exp_buf;         // [B][nbands][Mp]  published bottom rows {value bits, column+1}
+  int2* exp_mu;          // [B][nbands][Mg]  fwd: the publisher's offset per 8 columns {mu bits, group+1}
   int* ticket;           // [1]
-  int B, N, M, nbands, Mp;
+  int B, N, M, nbands, Mp, Mg;
   float gamma, bandwidth;
 };
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async4s(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
@@ -63,35 +80,54 @@ __device__ __forceinline__ void st_volatile_int2(int2* p, int2 v) {
 }
 __device__ __forceinline__ float ex2f_(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float lg2f_(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcpf_(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void st_stream4f2(float2* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// warp minimum of floats through one REDUX on order-preserving integer keys (+inf = "no value")
+__device__ __forceinline__ float warp_min_redux(float v) {
+  int k = __float_as_int(v);
+  k = k >= 0 ? k : (k ^ 0x7fffffff);
+  k = __reduce_min_sync(0xffffffffu, k);
+  k = k >= 0 ? k : (k ^ 0x7fffffff);
+  return __int_as_float(k);
+}
 
-constexpr int kRing = 4;                  // staged input tiles per matrix (power of two: ring index = col & 127)
+constexpr int kRing = 4;                  // staged input tiles (power of two: ring index = col & 127)
 constexpr int kRingCols = kRing * kTile;  // 128
 constexpr int kOutCols = 2 * kTile;       // result ring: two tiles
 
-// Stage one 32-column tile (columns c0.. of the possibly flipped grid) of a [N,M] matrix into the smem
-// ring sm[32][128] at ring slot (c0/32)&3.  Out-of-range elements are left untouched (never read by an
-// active lane).  FLIP stages the flipped grid: smem row i' holds matrix row N-1-(r0+i'); the 32 columns
-// are stored in matrix order (cp.async cannot reverse inside a 16-byte chunk) and the reader indexes
-// them with (col ^ 31).
-template <bool FLIP>
-__device__ __forceinline__ void stage_tile(float* sm, const float* __restrict__ mat, int N, int M, int r0, int c0,
+// Stage one 32-column tile (columns c0.. of the possibly flipped grid) of a [N,M] matrix of T (float or float2)
+// into the smem ring sm[32][128] at ring slot (c0/32)&3.  Out-of-range elements are left untouched (never read by
+// an active lane).  FLIP stages the flipped grid: smem row i' holds matrix row N-1-(r0+i'); the 32 columns are
+// stored in matrix order (cp.async cannot reverse inside a 16-byte chunk) and the reader indexes them with
+// (col ^ 31).
+template <bool FLIP, typename T>
+__device__ __forceinline__ void stage_tile(T* sm, const T* __restrict__ mat, int N, int M, int r0, int c0,
                                            int lane, bool vec) {
+  constexpr int kPer = 16 / (int)sizeof(T);            // elements per 16-byte chunk: 4 (float) or 2 (float2)
+  constexpr int kLanesPerRow = kTile / kPer;           // 8 or 16
+  constexpr int kRowsPerIt = 32 / kLanesPerRow;        // 4 or 2
   const int cbase = FLIP ? (M - c0 - kTile) : c0;
-  float* dst0 = sm + ((c0 >> 5) & (kRing - 1)) * kTile;
+  T* dst0 = sm + ((c0 >> 5) & (kRing - 1)) * kTile;
   if (vec) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {       // 8 lanes x 16 B cover one row; 4 rows per instruction
-      const int ri = it * 4 + (lane >> 3);
-      const int x = (lane & 7) * 4;
+    for (int it = 0; it < kBand / kRowsPerIt; ++it) {
+      const int ri = it * kRowsPerIt + lane / kLanesPerRow;
+      const int x = (lane % kLanesPerRow) * kPer;
       const int row = FLIP ? (N - 1 - (r0 + ri)) : (r0 + ri);
       const int col = cbase + x;
       if (row >= 0 && row < N) {
-        if (col >= 0 && col + 3 < M) {
+        if (col >= 0 && col + kPer - 1 < M) {
           cp_async16(dst0 + ri * kRingCols + x, mat + (int64_t)row * M + col);
         } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (col + e >= 0 && col + e < M) cp_async4s(dst0 + ri * kRingCols + x + e, mat + (int64_t)row * M + col + e);
+          for (int e = 0; e < kPer; ++e)
+            if (col + e >= 0 && col + e < M) {
+              if (sizeof(T) == 8) cp_async8(dst0 + ri * kRingCols + x + e, mat + (int64_t)row * M + col + e);
+              else cp_async4s(dst0 + ri * kRingCols + x + e, mat + (int64_t)row * M + col + e);
+            }
         }
       }
     }
@@ -99,30 +135,37 @@ __device__ __forceinline__ void stage_tile(float* sm, const float* __restrict__ 
     for (int ri = 0; ri < kBand; ++ri) {
       const int row = FLIP ? (N - 1 - (r0 + ri)) : (r0 + ri);
       const int col = cbase + lane;
-      if (row >= 0 && row < N && col >= 0 && col < M) cp_async4s(dst0 + ri * kRingCols + lane, mat + (int64_t)row * M + col);
+      if (row >= 0 && row < N && col >= 0 && col < M) {
+        if (sizeof(T) == 8) cp_async8(dst0 + ri * kRingCols + lane, mat + (int64_t)row * M + col);
+        else cp_async4s(dst0 + ri * kRingCols + lane, mat + (int64_t)row * M + col);
+      }
     }
   }
 }
 
-// Flush a finished 32-column result tile (ring sm[32][64], slot (c0/32)&1) with coalesced stores.
-template <bool FLIP>
-__device__ __forceinline__ void flush_tile(const float* sm, float* __restrict__ mat, int N, int M, int r0, int c0,
+// Flush a finished 32-column result tile (ring sm[32][64], slot (c0/32)&1) with coalesced 128-bit stores.
+template <bool FLIP, typename T>
+__device__ __forceinline__ void flush_tile(const T* sm, T* __restrict__ mat, int N, int M, int r0, int c0,
                                            int lane, bool vec) {
+  constexpr int kPer = 16 / (int)sizeof(T);
+  constexpr int kLanesPerRow = kTile / kPer;
+  constexpr int kRowsPerIt = 32 / kLanesPerRow;
   const int cbase = FLIP ? (M - c0 - kTile) : c0;
-  const float* src0 = sm + ((c0 >> 5) & 1) * kTile;
+  const T* src0 = sm + ((c0 >> 5) & 1) * kTile;
   if (vec) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int ri = it * 4 + (lane >> 3);
-      const int x = (lane & 7) * 4;
+    for (int it = 0; it < kBand / kRowsPerIt; ++it) {
+      const int ri = it * kRowsPerIt + lane / kLanesPerRow;
+      const int x = (lane % kLanesPerRow) * kPer;
       const int row = FLIP ? (N - 1 - (r0 + ri)) : (r0 + ri);
       const int col = cbase + x;
       if (row >= 0 && row < N) {
-        if (col >= 0 && col + 3 < M) {
-          st_stream4(mat + (int64_t)row * M + col, *reinterpret_cast<const float4*>(src0 + ri * kOutCols + x));
+        if (col >= 0 && col + kPer - 1 < M) {
+          const float4 v = *reinterpret_cast<const float4*>(src0 + ri * kOutCols + x);
+          st_stream4(reinterpret_cast<float*>(mat + (int64_t)row * M + col), v);
         } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
+          for (int e = 0; e < kPer; ++e)
             if (col + e >= 0 && col + e < M) mat[(int64_t)row * M + col + e] = src0[ri * kOutCols + x + e];
         }
       }
@@ -136,28 +179,27 @@ __device__ __forceinline__ void flush_tile(const float* sm, float* __restrict__ 
   }
 }
 
-template <bool BWD, bool PRUNE>
-__global__ void __launch_bounds__(256)
-softdtw_wave_kernel(SdtwParams P, int vec, int smem_per_warp) {
+// ------------------------------------------------------------------------------------------------ forward
+// R = D + softmin_gamma(diag, up, left)  (soft_dtw_cuda.py:65-72,196-204), values in units of gamma*ln2 relative to
+// the warp's offset mu; writes the softmin weights (up, left) of every cell and R[N-1,M-1].
+template <bool PRUNE, bool WRITE_R>
+__global__ void __launch_bounds__(224)
+softdtw_fwd_kernel(SdtwParams P, int vec, int smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int kGrp = BWD ? kGrpBwd : kGrpFwd;
+  constexpr int kGrp = kGrpFwd;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* sm = reinterpret_cast<float*>(smem_raw + (size_t)warp * smem_per_warp);
-  float* sD = sm;                                            // [32][128]
-  float* sR = BWD ? (sD + kBand * kRingCols) : nullptr;      // [32][128] (backward only)
-  float* sO = (BWD ? sR : sD) + kBand * kRingCols;           // [32][64]
+  float* sD = reinterpret_cast<float*>(smem_raw + (size_t)warp * smem_per_warp);      // [32][128]
+  float2* sO = reinterpret_cast<float2*>(sD + kBand * kRingCols);                      // [32][64] weights
   const float* sDl = sD + lane * kRingCols;
-  const float* sRl = BWD ? (sR + lane * kRingCols) : nullptr;
-  float* sOl = sO + lane * kOutCols;
+  float2* sOl = sO + lane * kOutCols;
   const int N = P.N, M = P.M;
   const int n_agents = P.B * P.nbands;
   const int n_tiles = (M + kTile - 1) / kTile;
-  const float ig2 = kLog2eF / P.gamma;                       // 1/gamma in log2 units
-  const float g_ln2 = P.gamma * kLn2F;
+  const float ig2 = (float)(kLog2e / (double)P.gamma);       // natural units -> units of gamma*ln2
+  const double unit = (double)P.gamma * kLn2;
   const float INF = CUDART_INF_F;
   const int steps = M + kBand - 1;
   const int k_last = (steps - 1) >> 5;
-  const int flipx = BWD ? (kTile - 1) : 0;                   // flipped tiles are stored in matrix order
 
   for (;;) {
     int tk = 0;
@@ -165,59 +207,45 @@ softdtw_wave_kernel(SdtwParams P, int vec, int smem_per_warp) {
     tk = __shfl_sync(0xffffffffu, tk, 0);
     if (tk >= n_agents) break;
     const int band = tk / P.B, b = tk - band * P.B;          // (band, sample) order
-    const int r0 = band * kBand;                             // first (flipped) row of this band
-    const int frow = r0 + lane;
-    const bool row_ok = frow < N;
-    const int row = BWD ? (N - 1 - frow) : frow;             // matrix row
+    const int r0 = band * kBand;
+    const int row = r0 + lane;
+    const bool row_ok = row < N;
     const float* Db = P.D + (int64_t)b * N * M;
-    float* Rb = P.R + (int64_t)b * N * M;
-    float* Ob = BWD ? (P.E + (int64_t)b * N * M) : Rb;
+    float2* Wb = P.W + (int64_t)b * N * M;
+    float* Rb = WRITE_R ? (P.R + (int64_t)b * N * M) : nullptr;
     int2* exp_mine = P.exp_buf + ((int64_t)b * P.nbands + band) * P.Mp;
+    int2* mu_mine = P.exp_mu + ((int64_t)b * P.nbands + band) * P.Mg;
     const int2* exp_up = band > 0 ? (P.exp_buf + ((int64_t)b * P.nbands + band - 1) * P.Mp) : nullptr;
+    const int2* mu_up_p = band > 0 ? (P.exp_mu + ((int64_t)b * P.nbands + band - 1) * P.Mg) : nullptr;
     const bool publish = (lane == kBand - 1) && (band + 1 < P.nbands);
-    // W of the upper band's bottom row (backward): R - D read straight from global, column index flipped
-    const float* upR = BWD && band > 0 ? (Rb + (int64_t)(N - r0) * M) : nullptr;
-    const float* upD = BWD && band > 0 ? (Db + (int64_t)(N - r0) * M) : nullptr;
 
     __syncwarp();
-    // prologue: tiles 0 and 1 (tile k+2 is staged when lane 0 enters tile k)
     int staged = 0;
-    for (; staged < 2 && staged < n_tiles; ++staged) {
-      stage_tile<BWD>(sD, Db, N, M, r0, staged * kTile, lane, vec);
-      if (BWD) stage_tile<BWD>(sR, Rb, N, M, r0, staged * kTile, lane, vec);
+    for (; staged < 2 && staged < n_tiles; ++staged) {       // prologue: tiles 0 and 1
+      stage_tile<false>(sD, Db, N, M, r0, staged * kTile, lane, vec);
       cp_commit();
     }
 
-    // Wavefront state.  Borders come from the initial values: before a lane's first cell its `left` is
-    // the left border and the upper lane still holds its own initial (border) value.
-    float my_v = BWD ? 0.0f : INF, my_w = -INF;              // this lane's latest cell
-    float up_v = my_v, up_w = -INF;                          // upper lane's cell one step ago (= diagonal)
-    if (band == 0 && lane == 0) {                            // the corner the recursion starts from
-      up_v = BWD ? P.gout[b * P.gout_stride] : 0.0f;
-      up_w = BWD ? Rb[(int64_t)(N - 1) * M + (M - 1)] : 0.0f;
-    }
-    float ab_v = BWD ? 0.0f : INF, ab_w = -INF;              // bottom row of the band above, kGrp columns
-    // export words of the band above are requested kDepth groups before they are needed (tag-in-data:
-    // {value, column+1}); lanes 0..kGrp-1 hold one column each
-    int2 nx[kDepth];
-    float nx_r[kDepth], nx_d[kDepth];
-#pragma unroll
-    for (int u = 0; u < kDepth; ++u) {
-      nx[u] = make_int2(0, 0); nx_r[u] = 0.0f; nx_d[u] = 0.0f;
-      const int col = u * kGrp + lane;
-      if (exp_up && lane < kGrp && col < M) {
-        nx[u] = ld_volatile_int2(exp_up + col);
-        if (BWD) { nx_r[u] = __ldcg(upR + (M - 1 - col)); nx_d[u] = __ldcg(upD + (M - 1 - col)); }
-      }
+    // Wavefront state (centred).  Borders come from the initial values: before a lane's first cell its `left` is
+    // the left border (+inf) and the upper lane still holds its own initial (border) value.
+    float my_v = INF, up_v = INF;
+    if (band == 0 && lane == 0) up_v = 0.0f;                 // R[-1,-1] = 0: the corner the recursion starts from
+    float mu = 0.0f;                                         // warp-uniform, integer-valued
+    float ab_v = INF;                                        // bottom row of the band above (lanes 0..kGrp-1)
+    // export words of the band above are requested one group before they are needed: lanes 0..kGrp-1 one column
+    // each, lane kGrp the group's mu word
+    int2 nx = make_int2(0, 0);
+    if (exp_up) {
+      if (lane < kGrp && lane < M) nx = ld_volatile_int2(exp_up + lane);
+      else if (lane == kGrp) nx = ld_volatile_int2(mu_up_p);
     }
 
     int p = 0;
-    int j = -lane;                                           // this lane's (flipped) column at step p
+    int j = -lane;                                           // this lane's column at step p
     for (int k = 0; k <= k_last; ++k) {
       // ---- once per 32 steps: lane 0 enters tile k
       if (staged < n_tiles && staged <= k + 2) {             // ring slot (k+2)&3 was tile k-2's: free
-        stage_tile<BWD>(sD, Db, N, M, r0, staged * kTile, lane, vec);
-        if (BWD) stage_tile<BWD>(sR, Rb, N, M, r0, staged * kTile, lane, vec);
+        stage_tile<false>(sD, Db, N, M, r0, staged * kTile, lane, vec);
         cp_commit();
         ++staged;
       }
@@ -228,88 +256,82 @@ softdtw_wave_kernel(SdtwParams P, int vec, int smem_per_warp) {
       }
       if (k >= 2 && k - 2 < n_tiles) {                       // tile k-2 is complete: flush it
         __syncwarp();
-        flush_tile<BWD>(sO, Ob, N, M, r0, (k - 2) * kTile, lane, vec);
+        flush_tile<false>(sO, Wb, N, M, r0, (k - 2) * kTile, lane, vec);
         __syncwarp();
       }
 #pragma unroll 1
       for (int gq = 0; gq < kTile / kGrp; ++gq) {
-        // ---- once per kGrp steps: take the kGrp band-above values requested kDepth groups ago (re-poll only
-        // if they had not been published yet), then request the group needed kDepth groups from now.
+        // ---- once per kGrp steps: take the band-above values (and the publisher's mu) requested one group ago,
+        // re-polling only what had not been published yet, then request the next group.
         if (exp_up && p < M) {
-          constexpr int us = 0;                              // kDepth == 1: a single request in flight
           const int col = p + lane;
-          const bool need = lane < kGrp && col < M;
-          int2 w = nx[us];
+          const bool need_v = lane < kGrp && col < M;
+          const bool need = need_v || lane == kGrp;
+          const int want = need_v ? col + 1 : (p >> 3) + 1;
+          const int2* addr = need_v ? (exp_up + col) : (mu_up_p + (p >> 3));
+          int2 w = nx;
           for (;;) {
-            if (__all_sync(0xffffffffu, !need || w.y == col + 1)) break;
-            if (need) w = ld_volatile_int2(exp_up + col);
+            if (__all_sync(0xffffffffu, !need || w.y == want)) break;
+            if (need) w = ld_volatile_int2(addr);
           }
-          ab_v = __int_as_float(w.x);
-          if (BWD) ab_w = (PRUNE && isinf(nx_r[us])) ? -INF : nx_r[us] - nx_d[us];
-          const int col2 = col + kDepth * kGrp;
-          if (lane < kGrp && col2 < M) {
-            nx[us] = ld_volatile_int2(exp_up + col2);
-            if (BWD) { nx_r[us] = __ldcg(upR + (M - 1 - col2)); nx_d[us] = __ldcg(upD + (M - 1 - col2)); }
-          }
+          const float mu_pub = __shfl_sync(0xffffffffu, __int_as_float(w.x), kGrp);
+          if (p == 0) mu = mu_pub;                           // adopt the publisher's frame: values start centred
+          ab_v = __int_as_float(w.x) + (mu_pub - mu);        // exact integer shift between the two frames
+          const int col2 = col + kGrp;
+          if (lane < kGrp && col2 < M) nx = ld_volatile_int2(exp_up + col2);
+          else if (lane == kGrp && p + kGrp < M) nx = ld_volatile_int2(mu_up_p + ((p + kGrp) >> 3));
+        }
+        // shift for the re-centring at the last step of this group: follows the minimum over the active lanes
+        float shift;
+        {
+          const bool act = row_ok && j > 0 && j <= M;        // has a cell of its own and has not run out
+          shift = warp_min_redux(act ? my_v : INF);
+          shift = (shift < 1e30f && shift > -1e30f) ? rintf(shift) : 0.0f;
         }
         // inputs of the next kGrp cells leave shared memory before the dependent chain starts
-        float dq[kGrp], rq[kGrp];
+        float dq[kGrp];
 #pragma unroll
-        for (int q = 0; q < kGrp; ++q) {
-          const int sc = ((j + q) & (kRingCols - 1)) ^ flipx;
-          dq[q] = sDl[sc];
-          rq[q] = BWD ? sRl[sc] : 0.0f;
-        }
+        for (int q = 0; q < kGrp; ++q) dq[q] = sDl[(j + q) & (kRingCols - 1)] * ig2;
         float pub[kGrp];
 #pragma unroll
         for (int q = 0; q < kGrp; ++q, ++p, ++j) {
+          if (q == kGrp - 1) {                               // re-centre: lane 31 is entering a column = 0 mod 8
+            my_v -= shift; up_v -= shift; ab_v -= shift; mu += shift;
+          }
           // upper neighbour: the upper lane's latest cell (its column equals ours); lane 0 takes the band above
           float nu_v = __shfl_up_sync(0xffffffffu, my_v, 1);
-          float nu_w = BWD ? __shfl_up_sync(0xffffffffu, my_w, 1) : 0.0f;
-          {
-            const float a_v = __shfl_sync(0xffffffffu, ab_v, q);
-            const float a_w = BWD ? __shfl_sync(0xffffffffu, ab_w, q) : 0.0f;
-            if (lane == 0) { nu_v = a_v; nu_w = a_w; }
-          }
-          const float d = dq[q];
+          const float a_v = __shfl_sync(0xffffffffu, ab_v, q);
+          if (lane == 0) nu_v = a_v;
           const bool active = row_ok && (unsigned)j < (unsigned)M;
-          float res_v, res_w = 0.0f;
-          if (!BWD) {
-            // R = D + softmin_gamma(diag, up, left)  (soft_dtw_cuda.py:65-72); left = my_v, diag = up_v.
-            // Without pruning every cell has a finite predecessor, so mn is finite and (mn - inf) is safe.
-            const float mn = fminf(fminf(up_v, nu_v), my_v);
-            const float s = ex2f_((mn - up_v) * ig2) + ex2f_((mn - nu_v) * ig2) + ex2f_((mn - my_v) * ig2);
-            res_v = d + (mn - g_ln2 * lg2f_(s));
-            if (PRUNE) {
-              if (mn == INF || fabsf((float)(row - j)) > P.bandwidth) res_v = INF;
-            }
-          } else {
-            // E = E_dn*a + E_right*b + E_diag*c, a,b,c = exp((W[.] - R[i,j]) / gamma)  (:100-108)
-            float r = rq[q];
-            if (PRUNE && isinf(r)) r = -INF;                 // :96-97 (only pruned cells hold +inf)
-            res_w = r - d;
-            const float a = ex2f_((nu_w - r) * ig2), bb = ex2f_((my_w - r) * ig2), c = ex2f_((up_w - r) * ig2);
-            res_v = nu_v * a + my_v * bb + up_v * c;
-            if (PRUNE) {
-              if (r == -INF) { res_v = 0.0f; res_w = -INF; }
-              if (fabsf((float)(row - (M - 1 - j))) > P.bandwidth) res_v = 0.0f;
-            }
+          // diag = up_v, up = nu_v, left = my_v.  Without pruning every cell has a finite predecessor.
+          const float mn = fminf(fminf(up_v, my_v), nu_v);
+          const float e_d = ex2f_(mn - up_v), e_u = ex2f_(mn - nu_v), e_l = ex2f_(mn - my_v);
+          const float s = e_d + e_u + e_l;
+          float res = dq[q] + (mn - lg2f_(s));
+          const float inv = rcpf_(s);
+          float2 wgt = make_float2(e_u * inv, e_l * inv);
+          if (PRUNE) {
+            if (mn == INF || fabsf((float)(row - j)) > P.bandwidth) { res = INF; wgt = make_float2(0.0f, 0.0f); }
           }
-          up_v = nu_v; up_w = nu_w;
+          up_v = nu_v;
           if (active) {
-            my_v = res_v; my_w = res_w;
-            sOl[(j & (kOutCols - 1)) ^ flipx] = res_v;
+            my_v = res;
+            sOl[j & (kOutCols - 1)] = wgt;
+            if (WRITE_R) Rb[(int64_t)row * M + j] = (float)(((double)mu + (double)res) * unit);
           }
-          pub[q] = res_v;
+          pub[q] = res;
         }
         // publish the band's bottom row for the band below: {value, column+1} in one 8-byte store per cell, after
-        // the group so that the volatile stores do not fence the chain's shared-memory traffic
+        // the group so that the volatile stores do not fence the chain's shared-memory traffic; the cell whose
+        // column is 0 mod 8 (the last of the group, computed after the re-centring) also publishes mu
         if (publish) {
 #pragma unroll
           for (int q = 0; q < kGrp; ++q) {
             const int jq = j - kGrp + q;
-            if ((unsigned)jq < (unsigned)M && row_ok)
+            if ((unsigned)jq < (unsigned)M) {
               st_volatile_int2(exp_mine + jq, make_int2(__float_as_int(pub[q]), jq + 1));
+              if (q == kGrp - 1) st_volatile_int2(mu_mine + (jq >> 3), make_int2(__float_as_int(mu), (jq >> 3) + 1));
+            }
           }
         }
       }
@@ -317,68 +339,226 @@ softdtw_wave_kernel(SdtwParams P, int vec, int smem_per_warp) {
     // flush the tiles not yet flushed inside the loop (at most two)
     __syncwarp();
     for (int k = (k_last - 1 > 0 ? k_last - 1 : 0); k < n_tiles; ++k)
-      flush_tile<BWD>(sO, Ob, N, M, r0, k * kTile, lane, vec);
+      flush_tile<false>(sO, Wb, N, M, r0, k * kTile, lane, vec);
     __syncwarp();
-    if (!BWD && band == P.nbands - 1) {
-      const float v = __shfl_sync(0xffffffffu, my_v, (N - 1) - r0);   // R[N-1, M-1]
-      if (lane == 0) P.out[b] = v;
+    if (band == P.nbands - 1) {
+      const float v = __shfl_sync(0xffffffffu, my_v, (N - 1) - r0);   // R[N-1, M-1] (centred)
+      if (lane == 0) P.out[b] = (float)(((double)mu + (double)v) * unit);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// Same sweep on the flipped grid (i' = N-1-i, j' = M-1-j).  Every cell turns its E into three messages
+// (E*Wu to the cell above it, E*Wl to the cell on its left, E*Wd to the diagonal one); a cell's E is the sum of the
+// three messages it receives (soft_dtw_cuda.py:100-108 with a, b, c read from the forward pass).
+__global__ void __launch_bounds__(160)
+softdtw_bwd_kernel(SdtwParams P, int vec, int smem_per_warp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kGrp = kGrpBwd;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2* sW = reinterpret_cast<float2*>(smem_raw + (size_t)warp * smem_per_warp);     // [32][128]
+  float* sO = reinterpret_cast<float*>(sW + kBand * kRingCols);                        // [32][64]
+  const float2* sWl = sW + lane * kRingCols;
+  float* sOl = sO + lane * kOutCols;
+  const int N = P.N, M = P.M;
+  const int n_agents = P.B * P.nbands;
+  const int n_tiles = (M + kTile - 1) / kTile;
+  const int steps = M + kBand - 1;
+  const int k_last = (steps - 1) >> 5;
+  constexpr int flipx = kTile - 1;                           // flipped tiles are stored in matrix order
+
+  for (;;) {
+    int tk = 0;
+    if (lane == 0) tk = atomicAdd(P.ticket, 1);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= n_agents) break;
+    const int band = tk / P.B, b = tk - band * P.B;
+    const int r0 = band * kBand;                             // first flipped row of this band
+    const int frow = r0 + lane;
+    const bool row_ok = frow < N;
+    const float2* Wb = P.W + (int64_t)b * N * M;
+    float* Eb = P.E + (int64_t)b * N * M;
+    int2* exp_mine = P.exp_buf + ((int64_t)b * P.nbands + band) * P.Mp;
+    const int2* exp_up = band > 0 ? (P.exp_buf + ((int64_t)b * P.nbands + band - 1) * P.Mp) : nullptr;
+    const bool publish = (lane == kBand - 1) && (band + 1 < P.nbands);
+    // weights of the upper band's bottom row (matrix row N - r0), read straight from global, column index flipped
+    const float2* upW = band > 0 ? (Wb + (int64_t)(N - r0) * M) : nullptr;
+
+    __syncwarp();
+    int staged = 0;
+    for (; staged < 2 && staged < n_tiles; ++staged) {
+      stage_tile<true>(sW, Wb, N, M, r0, staged * kTile, lane, vec);
+      cp_commit();
+    }
+
+    // messages: m_l = own cell -> left neighbour (same lane, next step); m_u / m_d = own cell -> the lane below
+    // (this step / next step).  in_d is the diagonal message received one step ago.
+    float m_u = 0.0f, m_d = 0.0f, m_l = 0.0f, in_d = 0.0f;
+    if (band == 0 && lane == 0) in_d = P.gout[b * P.gout_stride];      // E[N-1,M-1] = upstream gradient (:165)
+    float ab_u = 0.0f, ab_d = 0.0f;                          // messages of the band above (lanes 0..kGrp-1)
+    int2 nx = make_int2(0, 0);
+    float2 nx_w = make_float2(0.0f, 0.0f);
+    if (exp_up && lane < kGrp && lane < M) {
+      nx = ld_volatile_int2(exp_up + lane);
+      nx_w = __ldcg(upW + (M - 1 - lane));
+    }
+
+    int p = 0;
+    int j = -lane;                                           // this lane's flipped column at step p
+    for (int k = 0; k <= k_last; ++k) {
+      if (staged < n_tiles && staged <= k + 2) {
+        stage_tile<true>(sW, Wb, N, M, r0, staged * kTile, lane, vec);
+        cp_commit();
+        ++staged;
+      }
+      if (k < n_tiles) {
+        const int newer = staged - 1 - k;
+        if (newer >= 2) cp_wait<2>(); else if (newer == 1) cp_wait<1>(); else cp_wait<0>();
+        __syncwarp();
+      }
+      if (k >= 2 && k - 2 < n_tiles) {
+        __syncwarp();
+        flush_tile<true>(sO, Eb, N, M, r0, (k - 2) * kTile, lane, vec);
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int gq = 0; gq < kTile / kGrp; ++gq) {
+        if (exp_up && p < M) {
+          const int col = p + lane;
+          const bool need = lane < kGrp && col < M;
+          int2 w = nx;
+          for (;;) {
+            if (__all_sync(0xffffffffu, !need || w.y == col + 1)) break;
+            if (need) w = ld_volatile_int2(exp_up + col);
+          }
+          const float e_up = need ? __int_as_float(w.x) : 0.0f;
+          ab_u = e_up * nx_w.x;
+          ab_d = e_up * (1.0f - nx_w.x - nx_w.y);
+          const int col2 = col + kGrp;
+          if (lane < kGrp && col2 < M) {
+            nx = ld_volatile_int2(exp_up + col2);
+            nx_w = __ldcg(upW + (M - 1 - col2));
+          }
+        }
+        // weights of the next kGrp own cells leave shared memory before the dependent chain starts; cells outside
+        // the matrix get zero weights so that they emit no messages
+        float wu[kGrp], wl[kGrp], wd[kGrp];
+#pragma unroll
+        for (int q = 0; q < kGrp; ++q) {
+          const bool act = row_ok && (unsigned)(j + q) < (unsigned)M;
+          const float2 w = sWl[((j + q) & (kRingCols - 1)) ^ flipx];
+          wu[q] = act ? w.x : 0.0f;
+          wl[q] = act ? w.y : 0.0f;
+          wd[q] = act ? (1.0f - w.x - w.y) : 0.0f;
+        }
+        float pub[kGrp];
+#pragma unroll
+        for (int q = 0; q < kGrp; ++q, ++p, ++j) {
+          float nu_u = __shfl_up_sync(0xffffffffu, m_u, 1);
+          float nu_d = __shfl_up_sync(0xffffffffu, m_d, 1);
+          const float a_u = __shfl_sync(0xffffffffu, ab_u, q);
+          const float a_d = __shfl_sync(0xffffffffu, ab_d, q);
+          if (lane == 0) { nu_u = a_u; nu_d = a_d; }
+          const float e = nu_u + (m_l + in_d);
+          in_d = nu_d;
+          m_u = e * wu[q]; m_l = e * wl[q]; m_d = e * wd[q];
+          if (row_ok && (unsigned)j < (unsigned)M) sOl[(j & (kOutCols - 1)) ^ flipx] = e;
+          pub[q] = e;
+        }
+        if (publish) {
+#pragma unroll
+          for (int q = 0; q < kGrp; ++q) {
+            const int jq = j - kGrp + q;
+            if ((unsigned)jq < (unsigned)M)
+              st_volatile_int2(exp_mine + jq, make_int2(__float_as_int(pub[q]), jq + 1));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    for (int k = (k_last - 1 > 0 ? k_last - 1 : 0); k < n_tiles; ++k)
+      flush_tile<true>(sO, Eb, N, M, r0, k * kTile, lane, vec);
+    __syncwarp();
+  }
+}
+
+static size_t sdtw_scratch(int B, int N, int M) {
+  const size_t nb = (size_t)(N + kBand - 1) / kBand;
+  const size_t Mp = ((size_t)M + 3) / 4 * 4;
+  const size_t Mg = ((size_t)M + 7) / 8 + 1;
+  return 256 + (size_t)B * nb * (Mp + Mg) * sizeof(int2);
 }
 
 }  // namespace dae
 
 extern "C" size_t dae_softdtw_scratch_bytes(int B, int N, int M) {
   if (B < 0 || N < 0 || M < 0) return 0;
-  const size_t nb = (size_t)(N + dae::kBand - 1) / dae::kBand;
-  const size_t Mp = ((size_t)M + 3) / 4 * 4;
-  return 256 + (size_t)B * nb * Mp * sizeof(int2);
+  return dae::sdtw_scratch(B, N, M);
 }
 
-template <bool BWD>
-static int softdtw_launch(const float* D, float* R, float* E, float* out, const float* gout, int64_t gout_stride,
-                          int B, int N, int M, float gamma, float bandwidth, void* scratch, size_t scratch_bytes,
-                          cudaStream_t st) {
+static int softdtw_setup(dae::SdtwParams& P, int B, int N, int M, void* scratch, size_t scratch_bytes, cudaStream_t st) {
   using namespace dae;
-  if (!D || !R || B < 0 || N < 0 || M < 0 || !(gamma > 0.0f)) return DAE_E_BADARG;
-  if (B == 0 || N == 0 || M == 0) return 0;
-  if (!scratch || scratch_bytes < dae_softdtw_scratch_bytes(B, N, M)) return DAE_E_SCRATCH;
+  if (!scratch || scratch_bytes < sdtw_scratch(B, N, M)) return DAE_E_SCRATCH;
   if ((reinterpret_cast<uintptr_t>(scratch) & 255u) != 0) return DAE_E_ALIGN;
-  SdtwParams P;
-  P.D = D; P.R = R; P.E = E; P.out = out; P.gout = gout; P.gout_stride = gout_stride;
   P.B = B; P.N = N; P.M = M;
   P.nbands = (N + kBand - 1) / kBand;
   P.Mp = (M + 3) / 4 * 4;
+  P.Mg = (M + 7) / 8 + 1;
   P.ticket = reinterpret_cast<int*>(scratch);
   P.exp_buf = reinterpret_cast<int2*>(reinterpret_cast<char*>(scratch) + 256);
-  P.gamma = gamma; P.bandwidth = bandwidth;
-  DAE_CUDA(cudaMemsetAsync(scratch, 0, dae_softdtw_scratch_bytes(B, N, M), st));
-  const int smem_per_warp = ((BWD ? 2 : 1) * kBand * kRingCols + kBand * kOutCols) * 4;   // 24 KB / 40 KB
-  const int warps = BWD ? 5 : 8;
+  P.exp_mu = P.exp_buf + (size_t)B * P.nbands * P.Mp;
+  DAE_CUDA(cudaMemsetAsync(scratch, 0, sdtw_scratch(B, N, M), st));
+  return 0;
+}
+
+extern "C" int dae_softdtw_fwd(const float* D, int B, int N, int M, float gamma, float bandwidth, float* W,
+                               float* R, float* out, void* scratch, size_t scratch_bytes, void* stream) {
+  using namespace dae;
+  if (!D || !W || !out || B < 0 || N < 0 || M < 0 || !(gamma > 0.0f)) return DAE_E_BADARG;
+  if (B == 0 || N == 0 || M == 0) return 0;
+  if (!aligned16(W)) return DAE_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  SdtwParams P{};
+  P.D = D; P.W = reinterpret_cast<float2*>(W); P.R = R; P.out = out; P.gamma = gamma; P.bandwidth = bandwidth;
+  const int rc = softdtw_setup(P, B, N, M, scratch, scratch_bytes, st);
+  if (rc) return rc;
+  const int smem_per_warp = kBand * kRingCols * 4 + kBand * kOutCols * 8;               // 16 KB + 16 KB
+  const int warps = 7;
   const int smem = smem_per_warp * warps;
   const bool prune = bandwidth > 0.0f;
-  auto kern = prune ? softdtw_wave_kernel<BWD, true> : softdtw_wave_kernel<BWD, false>;
+  auto kern = prune ? (R ? softdtw_fwd_kernel<true, true> : softdtw_fwd_kernel<true, false>)
+                    : (R ? softdtw_fwd_kernel<false, true> : softdtw_fwd_kernel<false, false>);
   DAE_CUDA(ensure_dyn_smem(kern, smem));
   const int agents = B * P.nbands;
   int grid = (agents + warps - 1) / warps;
   if (grid > kNumSMs) grid = kNumSMs;                     // persistent: one CTA per SM, tickets do the rest
-  const int vec = aligned16(D) && aligned16(R) && (!BWD || aligned16(E)) && (M % 4 == 0);
+  const int vec = aligned16(D) && (M % 4 == 0);
   kern<<<grid, warps * 32, smem, st>>>(P, vec, smem_per_warp);
   DAE_LAUNCH_OK();
   return 0;
 }
 
-extern "C" int dae_softdtw_fwd(const float* D, int B, int N, int M, float gamma, float bandwidth, float* R,
-                               float* out, void* scratch, size_t scratch_bytes, void* stream) {
-  if (!out) return DAE_E_BADARG;
-  return softdtw_launch<false>(D, R, nullptr, out, nullptr, 0, B, N, M, gamma, bandwidth, scratch, scratch_bytes,
-                               (cudaStream_t)stream);
-}
-
-extern "C" int dae_softdtw_bwd(const float* D, const float* R, const float* gout, int64_t gout_stride, int B, int N,
-                               int M, float gamma, float bandwidth, float* E, void* scratch, size_t scratch_bytes,
-                               void* stream) {
-  if (!E || !gout) return DAE_E_BADARG;
-  return softdtw_launch<true>(D, const_cast<float*>(R), E, nullptr, gout, gout_stride, B, N, M, gamma, bandwidth,
-                              scratch, scratch_bytes, (cudaStream_t)stream);
+extern "C" int dae_softdtw_bwd(const float* W, const float* gout, int64_t gout_stride, int B, int N, int M,
+                               float* E, void* scratch, size_t scratch_bytes, void* stream) {
+  using namespace dae;
+  if (!W || !E || !gout || B < 0 || N < 0 || M < 0) return DAE_E_BADARG;
+  if (B == 0 || N == 0 || M == 0) return 0;
+  if (!aligned16(W)) return DAE_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  SdtwParams P{};
+  P.W = reinterpret_cast<float2*>(const_cast<float*>(W)); P.E = E; P.gout = gout; P.gout_stride = gout_stride;
+  const int rc = softdtw_setup(P, B, N, M, scratch, scratch_bytes, st);
+  if (rc) return rc;
+  const int smem_per_warp = kBand * kRingCols * 8 + kBand * kOutCols * 4;               // 32 KB + 8 KB
+  const int warps = 5;
+  const int smem = smem_per_warp * warps;
+  DAE_CUDA(ensure_dyn_smem(softdtw_bwd_kernel, smem));
+  const int agents = B * P.nbands;
+  int grid = (agents + warps - 1) / warps;
+  if (grid > kNumSMs) grid = kNumSMs;
+  const int vec = aligned16(E) && (M % 4 == 0);
+  softdtw_bwd_kernel<<<grid, warps * 32, smem, st>>>(P, vec, smem_per_warp);
+  DAE_LAUNCH_OK();
+  return 0;
 }

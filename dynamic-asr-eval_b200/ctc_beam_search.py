@@ -32,7 +32,7 @@ class Beam:
     __repr__ = __str__
 
 
-LanguageModel = NGramLM           # the `language_model=` argument type of this build
+LanguageModel = NGramLM           # implements get_initial_state() / __call__ of ctc_beam_search.py:45-87
 
 
 class _Search:
@@ -51,7 +51,8 @@ class _Search:
         self.dev = dev
         T, C = self.lp.shape
         if blank_id != C - 1:
-            raise _C.DaeError(f"blank_id must be the last class (got {blank_id}, C={C}); remap the posteriors")
+            raise _C.DaeError(f"blank_id must be the last class (got {blank_id}, C={C}); for blank-first posteriors "
+                              "(wav2vec2, blank 0) use dae.ctc_beam_search.blank_first_to_last(log_probs)")
         if not 1 <= beam_width <= MAX_BEAMS:
             raise _C.DaeError(f"beam_width must be in 1..{MAX_BEAMS}")
         self.T, self.C = T, C
@@ -134,15 +135,25 @@ class _Search:
         return out
 
 
+def blank_first_to_last(log_probs):
+    """Re-lay blank-first posteriors (HF wav2vec2: blank/pad id 0, wav2vec2/tedlium/run.py:123) for this class,
+    which assumes ``blank_id == vocab_size`` (lcasr/lib.py:64) and never expands class 0 (ctc_beam_search.py:242):
+    [T,C] -> [T,C+1] = [-inf, lp[:,1:], lp[:,0]].  Token ids keep their meaning (class i stays class i for i >= 1),
+    the new blank id is C, so ``tokenizer.vocab_size()`` must report C."""
+    lp = torch.as_tensor(log_probs)
+    pad = torch.full_like(lp[..., :1], float("-inf"))
+    return torch.cat([pad, lp[..., 1:], lp[..., :1]], dim=-1).contiguous()
+
+
 def beam_search_batch(log_probs, seg_offsets, language_model, beam_width, alpha=0.4, beta=0.4, blank_id=None,
                       blank_penalty=0.0, repitition_penalty=0.0, top_am_threshold=-6, prune_less_than_val=None,
-                      n_best=1):
+                      n_best=1, dense_lm=True):
     """Decode independent segments of ``log_probs`` [total_T, C] in ONE launch (one CTA per segment).
     Returns, per segment, the n_best hypotheses as (score, token ids, start frames, ends_in_blank)."""
     lp = torch.as_tensor(log_probs)
     s = _Search(lp, seg_offsets, language_model, beam_width, alpha, beta,
                 lp.shape[-1] - 1 if blank_id is None else blank_id, blank_penalty, repitition_penalty,
-                top_am_threshold, prune_less_than_val, n_best=n_best)
+                top_am_threshold, prune_less_than_val, n_best=n_best, dense_lm=dense_lm)
     s.run_all()
     return s.results()
 
@@ -150,7 +161,9 @@ def beam_search_batch(log_probs, seg_offsets, language_model, beam_width, alpha=
 class BeamSearch:
     def __init__(self, tokenizer, beam_width, log_probs, language_model, alpha=0.4, beta=0.4, blank_id=128,
                  blank_penalty=0.0, repitition_penalty=0.0, top_am_threshold=-6, max_cache_length=-1, debug=False,
-                 prune_less_than_val=None, cache_init=None):
+                 prune_less_than_val=None, cache_init=None, dense_lm=True):
+        """Signature of lcasr/ctc_beam_search.py:90-125 plus ``dense_lm``: True = serve LM queries from the dense
+        row/next expansion when it fits in 2 GB of HBM (else walk the trie), False = always walk the trie."""
         self.tokenizer = tokenizer
         self.beam_width = beam_width
         self.vocab_size = tokenizer.vocab_size()
@@ -163,6 +176,7 @@ class BeamSearch:
         self.blank_penalty, self.repitition_penalty = blank_penalty, repitition_penalty
         self.top_am_threshold, self.prune_less_than_val = top_am_threshold, prune_less_than_val
         self.max_cache_length, self.debug, self.cache_init = max_cache_length, debug, cache_init
+        self.dense_lm = dense_lm
         if blank_id != self.vocab_size:
             raise _C.DaeError("BeamSearch assumes blank_id == tokenizer.vocab_size() (lcasr/lib.py:64)")
         self._s = None
@@ -171,7 +185,7 @@ class BeamSearch:
         if self._s is None:
             self._s = _Search(self.log_probs, None, self.language_model, self.beam_width, self.alpha, self.beta,
                               self.blank_id, self.blank_penalty, self.repitition_penalty, self.top_am_threshold,
-                              self.prune_less_than_val)
+                              self.prune_less_than_val, dense_lm=self.dense_lm)
         return self._s
 
     def _refresh(self):

@@ -27,7 +27,7 @@ import torch
 import torch.nn as nn
 
 from . import _C, prof
-from .augment import SpecAugment, cutout
+from .augment import SpecAugment, add_random_noise, cutout, frame_shuffle
 from .ctc import CTCLoss
 from .greedy import GreedyCTCDecoder, greedy_ids_device
 from .optim import MADGRAD
@@ -88,21 +88,8 @@ def prepare_chunks(spec, seq_len, overlap):
     return training_data, list(training_data.keys())
 
 
-def frame_shuffle(spec, time_dimension=False, freq_dimension=False):
-    """lcasr/lib.py:81-84 (device tensors work as is)."""
-    if time_dimension:
-        spec = spec[:, :, torch.randperm(spec.shape[-1], device=spec.device)]
-    if freq_dimension:
-        spec = spec[:, torch.randperm(spec.shape[-2], device=spec.device), :]
-    return spec
-
-
-def add_random_noise(spec, noise_factor):
-    """lcasr/lib.py:379-382."""
-    if noise_factor == 0:
-        return spec
-    noise = torch.normal(0, std=spec.std().item(), size=spec.shape, device=spec.device)
-    return spec + noise * noise_factor
+# frame_shuffle (lcasr/lib.py:81-84) and add_random_noise (:379-382) live in dae/augment.py: host-drawn
+# randomness in the reference's order, gather / streaming kernels on the device.
 
 
 def _freeze(model, args):
@@ -240,7 +227,7 @@ def dynamic_eval_ctc_loss(
             if frame_shuffle_args['time_dimension'] or frame_shuffle_args['freq_dimension']:
                 audio_chunk[:num_negatives] = frame_shuffle(audio_chunk[:num_negatives], **frame_shuffle_args)
             if random_noise:
-                audio_chunk[:num_negatives] = add_random_noise(audio_chunk[:num_negatives], random_noise)
+                add_random_noise(audio_chunk[:num_negatives], random_noise)   # in place on the augmented copy
             if cutout_args['num_rectangles']:
                 cutout(audio_chunk[:num_negatives], **cutout_args)      # in place, lib.py:544
             out = model(audio_signal=audio_chunk)
@@ -522,7 +509,9 @@ def load_beamsearch(path: str, alpha: float = 0.45, beta: float = 1.53, prune_le
         from .standin import SyntheticTokenizer
         tokenizer = SyntheticTokenizer()
     V = vocab_size or tokenizer.vocab_size()
-    language_model = NGramLM.from_arpa(path, V, bos_id=tokenizer.bos_id() if bos_id is None else bos_id)
+    if bos_id is None:
+        bos_id = tokenizer.bos_id() if hasattr(tokenizer, 'bos_id') else -1   # sentencepiece without bos: -1
+    language_model = NGramLM.from_arpa(path, V, bos_id=bos_id)
     return partial(beam_search.BeamSearch, language_model=language_model, tokenizer=tokenizer, blank_id=V,
                    alpha=alpha, beta=beta, debug=False, prune_less_than_val=prune_less_than_val,
                    top_am_threshold=top_am_threshold, max_cache_length=128)

@@ -118,11 +118,25 @@ def read_arpa(path, word_to_id=None, bos_id=0):
     return order, grams
 
 
-class NGramLM:
-    """Flat-trie n-gram LM.  ``language_model=`` argument of dae.ctc_beam_search.BeamSearch."""
+def bos_token(vocab_size, bos_id):
+    """Token id that stands for ``<s>`` inside the trie (see NGramLM.__init__)."""
+    return int(bos_id) if bos_id is not None and 0 <= int(bos_id) < int(vocab_size) else int(vocab_size)
 
-    def __init__(self, grams, order, vocab_size, bos_id=0, unk_logprob10=-10.0):
+
+class NGramLM:
+    """Flat-trie n-gram LM.  ``language_model=`` argument of dae.ctc_beam_search.BeamSearch; also implements the
+    reference's ``LanguageModel`` duck type (lcasr/ctc_beam_search.py:45-87): ``bos_id``, ``get_initial_state()``
+    and ``__call__(input_ids, input_lengths, states)``, so code written against that interface (including the
+    reference's own BeamSearch class) can be driven by the HBM trie.  Neural LMs are not supported."""
+
+    def __init__(self, grams, order, vocab_size, bos_id=0, unk_logprob10=-10.0, device=None):
+        """``grams``: {token-id tuple: (log10 p, log10 backoff or None)} with the sentence-start token written as
+        ``bos_token(vocab_size, bos_id)``.  ``bos_id`` is what the caller's tokenizer reports (``Beam.lm_sequence[0]``,
+        lcasr/ctc_beam_search.py:133); a tokenizer without bos (sentencepiece returns -1) gets the reserved id
+        ``vocab_size`` inside the trie, which no search candidate can ever produce (it is the blank class)."""
         self.order, self.vocab_size, self.bos_id = int(order), int(vocab_size), int(bos_id)
+        self.bos_tok = bos_token(vocab_size, bos_id)
+        self.device = torch.device(device) if device is not None else None
         self.unk_lp = np.float32(unk_logprob10 * LN10)
         by_depth = [[] for _ in range(order + 1)]
         for ng in grams:
@@ -162,9 +176,60 @@ class NGramLM:
         self._dev = {}
 
     @classmethod
-    def from_arpa(cls, path, vocab_size, bos_id=0, word_to_id=None, unk_logprob10=-10.0):
-        order, grams = read_arpa(path, word_to_id, bos_id)
-        return cls(grams, order, vocab_size, bos_id, unk_logprob10)
+    def from_arpa(cls, path, vocab_size, bos_id=0, word_to_id=None, unk_logprob10=-10.0, device=None):
+        order, grams = read_arpa(path, word_to_id, bos_token(vocab_size, bos_id))
+        return cls(grams, order, vocab_size, bos_id, unk_logprob10, device=device)
+
+    # ---- LanguageModel duck type (lcasr/ctc_beam_search.py:45-87) -------------------------------------------
+    # The "KV cache" of the reference is the token history here: state = {'cache': float32 [1,1,B,1,N,1] holding
+    # the LM sequence of every beam (what BeamSearch.step pads, rearranges and slices, :284-312,172-191),
+    # 'cache_lengths': int64 [B]}.  Rows are computed on the device by dae_ngram_rows and returned on the CPU,
+    # as the reference's wrapper does (:74,87).
+    def to(self, device):
+        self.device = torch.device(device)
+        return self
+
+    def _rows(self, histories):
+        from . import _C
+        dev = self.device if self.device is not None else torch.device("cuda")
+        if dev.type != "cuda" or not torch.cuda.is_available():
+            raise _C.DaeError("NGramLM scoring needs a CUDA device: there is no CPU path")
+        a = self.device_arrays(dev)
+        st = torch.tensor([self.state_of(h) for h in histories], dtype=torch.int32).to(dev)
+        row = torch.empty((len(histories), self.vocab_size), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _C.lib().dae_ngram_rows(a["tok"].data_ptr(), a["logp"].data_ptr(), a["bo"].data_ptr(),
+                                         a["fail"].data_ptr(), a["cb"].data_ptr(), a["depth"].data_ptr(),
+                                         self.n_nodes, self.order, float(self.unk_lp), self.vocab_size,
+                                         st.data_ptr(), len(histories), row.data_ptr(), None, _C.stream_ptr(dev))
+        _C.check(rc, "dae_ngram_rows")
+        return row.cpu()
+
+    @staticmethod
+    def _pack_state(histories):
+        n = max(len(h) for h in histories)
+        cache = torch.zeros(1, 1, len(histories), 1, n, 1)
+        for b, h in enumerate(histories):
+            cache[0, 0, b, 0, :len(h), 0] = torch.tensor(h, dtype=torch.float32)
+        return {'cache': cache, 'cache_lengths': torch.LongTensor([len(h) for h in histories])}
+
+    def get_initial_state(self):
+        """-> (log p(. | <s>) [V] on the CPU, state)   (ctc_beam_search.py:70-74)."""
+        h = [self.bos_tok]
+        return self._rows([h])[0], self._pack_state([h])
+
+    def __call__(self, input_ids, input_lengths=None, states=None):
+        """input_ids [nb,1] = the token each beam just took; states = padded history batch ->
+        (log-probs [nb,1,V] on the CPU, new states)   (ctc_beam_search.py:83-87)."""
+        nb = int(input_ids.shape[0])
+        hists = []
+        for b in range(nb):
+            past = []
+            if states is not None:
+                n = int(states['cache_lengths'][b])
+                past = [int(x) for x in states['cache'][0, 0, b, 0, :n, 0].tolist()]
+            hists.append(past + [int(input_ids[b, -1])])
+        return self._rows(hists)[:, None, :], self._pack_state(hists)
 
     def nbytes(self):
         return sum(a.nbytes for a in (self.tok, self.logp, self.bo, self.depth, self.fail, self.cb))
@@ -203,7 +268,8 @@ class NGramLM:
     # host-side state helpers (index arithmetic only; scoring happens on the device)
     def state_of(self, history):
         """Trie node of the longest suffix of ``history`` (at most order-1 tokens) that is a node."""
-        h = tuple(history)[-(self.order - 1):] if self.order > 1 else ()
+        h = tuple(self.bos_tok if (t == self.bos_id and t != self.bos_tok) else t for t in history)
+        h = h[-(self.order - 1):] if self.order > 1 else ()
         for s in range(len(h) + 1):
             j = self._ids.get(h[s:])
             if j is not None:

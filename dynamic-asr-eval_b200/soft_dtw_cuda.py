@@ -1,10 +1,12 @@
-"""soft-DTW with the reference module's API (lcasr_nemo/soft_dtw_cuda.py), on the dae wavefront kernel.
+"""soft-DTW with the reference module's API (lcasr_nemo/soft_dtw_cuda.py), on the dae wavefront kernels.
 
 ``SoftDTW(use_cuda, gamma, normalize, bandwidth, dist_func)(X, Y) -> [B]`` (:273-352) and
 ``_SoftDTWCUDA.apply(D, gamma, bandwidth) -> [B]`` (:114-174) keep their signatures.  Unlike the
 reference there is no 1024-frame cap and no silent CPU fallback (:312-314): every length runs on the
-GPU, and CPU tensors are an error.  R is kept unpadded ([B,N,M], the interior of the reference's
-[B,N+2,M+2]); the backward pass writes ``grad_output * E`` in one pass.
+GPU, and CPU tensors are an error.  What the forward pass saves for the backward pass is not the fp32 R
+matrix of the reference (:144) but the per-cell softmin weights ``W`` [B,N,M,2] — the coefficients a, b, c of
+the reference's backward recurrence (:100-103) — so the backward pass is multiply-add only and the gradient is
+good to ~1e-6 of its scale at 4096x4096 (the reference's fp32 R limits its own to ~1e-4 there).
 """
 import torch
 
@@ -16,39 +18,41 @@ def _scratch(B, N, M, dev):
     return torch.empty(n, dtype=torch.uint8, device=dev), n
 
 
-def softdtw_forward(D, gamma, bandwidth=0.0):
-    """D [B,N,M] fp32 CUDA -> (value [B], R [B,N,M])."""
+def softdtw_forward(D, gamma, bandwidth=0.0, want_R=False):
+    """D [B,N,M] fp32 CUDA -> (value [B], W [B,N,M,2] softmin weights, R [B,N,M] or None)."""
     _C.require_cuda(D, "D")
     D = D.detach()
     if D.dtype != torch.float32 or not D.is_contiguous():
         D = D.float().contiguous()
     B, N, M = D.shape
     dev = D.device
-    R = torch.empty_like(D)
+    W = torch.empty((B, N, M, 2), dtype=torch.float32, device=dev)
+    R = torch.empty_like(D) if want_R else None
     out = torch.empty(B, dtype=torch.float32, device=dev)
     scratch, n = _scratch(B, N, M, dev)
     with torch.cuda.device(dev), prof.span("softdtw_fwd", 2 * B * N * M * 4):
-        rc = _C.lib().dae_softdtw_fwd(D.data_ptr(), B, N, M, float(gamma), float(bandwidth), R.data_ptr(),
-                                      out.data_ptr(), scratch.data_ptr(), n, _C.stream_ptr(dev))
+        rc = _C.lib().dae_softdtw_fwd(D.data_ptr(), B, N, M, float(gamma), float(bandwidth), W.data_ptr(),
+                                      _C.ptr(R), out.data_ptr(), scratch.data_ptr(), n, _C.stream_ptr(dev))
     _C.check(rc, "dae_softdtw_fwd")
-    return out, R, D
+    return out, W, R
 
 
-def softdtw_backward(D, R, grad_out, gamma, bandwidth=0.0):
-    """-> grad_out[b] * E [B,N,M] (soft_dtw_cuda.py:147-174)."""
-    B, N, M = D.shape
-    dev = D.device
+def softdtw_backward(W, grad_out):
+    """-> grad_out[b] * E [B,N,M] (soft_dtw_cuda.py:147-174) from the forward pass's weights."""
+    _C.require_cuda(W, "W")
+    B, N, M, _ = W.shape
+    dev = W.device
     g = grad_out.detach().to(torch.float32).reshape(-1)
     if g.numel() == 1 and B > 1:
         g_stride = 0
     else:
         g = g.contiguous()
         g_stride = 1
-    E = torch.empty_like(D)
+    E = torch.empty((B, N, M), dtype=torch.float32, device=dev)
     scratch, n = _scratch(B, N, M, dev)
     with torch.cuda.device(dev), prof.span("softdtw_bwd", 3 * B * N * M * 4):
-        rc = _C.lib().dae_softdtw_bwd(D.data_ptr(), R.data_ptr(), g.data_ptr(), g_stride, B, N, M, float(gamma),
-                                      float(bandwidth), E.data_ptr(), scratch.data_ptr(), n, _C.stream_ptr(dev))
+        rc = _C.lib().dae_softdtw_bwd(W.data_ptr(), g.data_ptr(), g_stride, B, N, M, E.data_ptr(),
+                                      scratch.data_ptr(), n, _C.stream_ptr(dev))
     _C.check(rc, "dae_softdtw_bwd")
     return E
 
@@ -56,15 +60,15 @@ def softdtw_backward(D, R, grad_out, gamma, bandwidth=0.0):
 class _SoftDTWCUDA(torch.autograd.Function):
     @staticmethod
     def forward(ctx, D, gamma, bandwidth):
-        out, R, Dc = softdtw_forward(D, gamma, bandwidth)
-        ctx.save_for_backward(Dc, R)
-        ctx.gamma, ctx.bandwidth, ctx.in_dtype = float(gamma), float(bandwidth), D.dtype
+        out, W, _ = softdtw_forward(D, gamma, bandwidth)
+        ctx.save_for_backward(W)
+        ctx.in_dtype = D.dtype
         return out.to(D.dtype)
 
     @staticmethod
     def backward(ctx, grad_output):
-        D, R = ctx.saved_tensors
-        E = softdtw_backward(D, R, grad_output, ctx.gamma, ctx.bandwidth)
+        W, = ctx.saved_tensors
+        E = softdtw_backward(W, grad_output)
         return E.to(ctx.in_dtype), None, None
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DAE_ABI_VERSION 1
+#define DAE_ABI_VERSION 2
 
 #define DAE_E_BADARG   (-1)  /* NULL pointer, negative size, ...                      */
 #define DAE_E_TOOBIG   (-2)  /* a dimension exceeds what the kernel supports          */
@@ -96,6 +96,24 @@ int dae_cutout(float* x, int64_t sF, int F, int T, const int32_t* rects_host, in
                void* scratch, size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (f-3) frame shuffle and additive noise on the augmented window; randomness is host-drawn by the caller.
+ * replaces: frame_shuffle() at lcasr/lib.py:81-84 (called at :542) and add_random_noise() at :379-382 (:543).
+ * dae_frame_shuffle: out[f,t] = x[perm_f[f], perm_t[t]]; perm_t [T] / perm_f [F] int32 DEVICE arrays drawn with
+ *            torch.randperm in the reference's order (time first, then frequency), NULL = identity; out [F,T]
+ *            contiguous, must not alias x.
+ * dae_add_noise:     x += (z * std(x)) * noise_factor in place, every product rounded to fp32 on its own (the
+ *            reference's tensor ops); z [F,T] contiguous DEVICE = the standard-normal field behind the reference's
+ *            torch.normal(0, std, size) draw (bitwise z*std, verified); std = unbiased standard deviation of x
+ *            (fp64 moments, fixed order, rounded once), also written to std_out (may be NULL).
+ *            scratch: dae_noise_scratch_bytes() bytes, 256-aligned.
+ * ------------------------------------------------------------------------------------ */
+int dae_frame_shuffle(const float* x, int64_t sF, int F, int T, const int32_t* perm_t, const int32_t* perm_f,
+                      float* out, void* stream);
+size_t dae_noise_scratch_bytes(void);
+int dae_add_noise(float* x, int64_t sF, int F, int T, const float* z, float noise_factor,
+                  void* scratch, size_t scratch_bytes, float* std_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * (1) CTC loss + gradient (torch.nn.CTCLoss semantics, zero_infinity=False).
  * replaces: torch.nn.CTCLoss(blank, reduction='sum')(...) and its backward at
  *           lcasr/lib.py:492,575-579 (AWMC: :250,324-331; finetune: earnings_finetune/train.py:259).
@@ -147,19 +165,23 @@ int dae_stitch(const float* lp, int C, const int64_t* win_off, const int64_t* wi
  *           compute_softdtw_backward_cuda at lcasr_nemo/soft_dtw_cuda.py:33-111,114-174, and the CPU
  *           kernels :184-239 the reference falls back to above 1024 frames (:312-314).
  * D    [B,N,M] fp32 contiguous cost matrices
- * R    [B,N,M] fp32: R[b,i,j] = D[b,i,j] + softmin_gamma(R[i-1,j-1], R[i-1,j], R[i,j-1]) with the
- *      reference's borders (R[-1,-1] = 0, other border cells +inf); +inf where |i-j| > bandwidth > 0.
- *      This is the interior R[:,1:N+1,1:M+1] of the reference's padded array.
- * out  [B] = R[b,N-1,M-1] (the soft-DTW value, the reference's R[:, -2, -2])
- * bwd: E [B,N,M] = gout[b] * dR[N-1,M-1]/dD  (the reference's grad_output * E[:,1:N+1,1:M+1]);
+ * fwd: R[b,i,j] = D[b,i,j] + softmin_gamma(R[i-1,j-1], R[i-1,j], R[i,j-1]) with the reference's borders
+ *      (R[-1,-1] = 0, other border cells +inf); +inf where |i-j| > bandwidth > 0.
+ *   out  [B] = R[b,N-1,M-1] (the soft-DTW value, the reference's R[:, -2, -2])
+ *   W    [B,N,M,2] fp32, 16-byte aligned: per cell the softmin weights of its `up` (i-1,j) and `left` (i,j-1)
+ *        predecessors; the `diag` weight is 1 - up - left.  These are the reference's backward coefficients
+ *        a, b, c of :100-103 (a at cell (i,j) = W[i+1,j].up, b = W[i,j+1].left, c = 1 - both of W[i+1,j+1]);
+ *        this is what the forward pass saves for the backward pass instead of the reference's fp32 R (:144).
+ *   R    [B,N,M] fp32 or NULL: the interior R[:,1:N+1,1:M+1] of the reference's padded array, written only
+ *        when asked for (the value and the gradient do not need it).
+ * bwd: E [B,N,M] = gout[b] * dR[N-1,M-1]/dD  (the reference's grad_output * E[:,1:N+1,1:M+1], :172-174);
  *      gout[b*gout_stride] is the upstream gradient of out[b].
  * scratch: dae_softdtw_scratch_bytes() bytes, 256-byte aligned; zeroed by the call itself.
  * ------------------------------------------------------------------------------------ */
 size_t dae_softdtw_scratch_bytes(int B, int N, int M);
 int dae_softdtw_fwd(const float* D, int B, int N, int M, float gamma, float bandwidth,
-                    float* R, float* out, void* scratch, size_t scratch_bytes, void* stream);
-int dae_softdtw_bwd(const float* D, const float* R, const float* gout, int64_t gout_stride,
-                    int B, int N, int M, float gamma, float bandwidth,
+                    float* W, float* R, float* out, void* scratch, size_t scratch_bytes, void* stream);
+int dae_softdtw_bwd(const float* W, const float* gout, int64_t gout_stride, int B, int N, int M,
                     float* E, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
@@ -188,6 +210,13 @@ size_t dae_beam_scratch_bytes(int n_seg, int arena_cap);
 int dae_ngram_expand(const int32_t* lm_tok, const float* lm_logp, const float* lm_bo, const int32_t* lm_fail,
                      const int32_t* lm_cb, const int32_t* lm_depth, int lm_nodes, int lm_order, float lm_unk_lp,
                      int vocab, int n_ctx, float* row, int32_t* next, void* stream);
+/* Rows for an explicit list of LM states: row[j*vocab + w] = log p(w | states[j]), next[j*vocab + w] = successor
+ * state (next may be NULL).  replaces: LanguageModel.get_initial_state / __call__ at
+ * lcasr/ctc_beam_search.py:70-87 (one Transformer-LM forward per batch of beams there).  states [n_states] int32
+ * device; out-of-range states are scored from the root. */
+int dae_ngram_rows(const int32_t* lm_tok, const float* lm_logp, const float* lm_bo, const int32_t* lm_fail,
+                   const int32_t* lm_cb, const int32_t* lm_depth, int lm_nodes, int lm_order, float lm_unk_lp,
+                   int vocab, const int32_t* states, int n_states, float* row, int32_t* next, void* stream);
 int dae_beam_search(const float* lp, const int32_t* seg_offsets, int n_seg, int C, int blank,
                     int beam_width, float alpha, float beta, float top_am_threshold,
                     float prune_less_than_val, int has_prune, float blank_penalty, float repetition_penalty,

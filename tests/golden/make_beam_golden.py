@@ -27,34 +27,10 @@ sys.path.insert(0, "/root/reference/lcasr")
 import ctc_beam_search as ref  # noqa: E402
 
 from dae.ngram import read_arpa, write_synthetic_arpa  # noqa: E402
-from oracle.beam_oracle import BeamSearchOracle, NGramOracle, peaky_log_probs  # noqa: E402
+from oracle.beam_oracle import BeamSearchOracle, NGramOracle, NGramOracleLM, peaky_log_probs  # noqa: E402
 
 
-class RefLMAdapter:
-    """LanguageModel duck type (ctc_beam_search.py:45-87): history rides in cache[0,0,b,0,:,0]."""
-
-    def __init__(self, ng):
-        self.ng, self.bos_id = ng, ng.bos_id
-
-    def _state(self, hists):
-        n = max(len(h) for h in hists)
-        cache = torch.zeros(1, 1, len(hists), 1, n, 1)
-        for b, h in enumerate(hists):
-            cache[0, 0, b, 0, :len(h), 0] = torch.tensor(h, dtype=torch.float32)
-        return {'cache': cache, 'cache_lengths': torch.LongTensor([len(h) for h in hists])}
-
-    def get_initial_state(self):
-        h = [self.bos_id]
-        return torch.from_numpy(self.ng.row(h)), self._state([h])
-
-    def __call__(self, input_ids, input_lengths, states):
-        nb = input_ids.shape[0]
-        hists = []
-        for b in range(nb):
-            n = int(states['cache_lengths'][b])
-            hists.append([int(x) for x in states['cache'][0, 0, b, 0, :n, 0].tolist()] + [int(input_ids[b, 0])])
-        rows = torch.stack([torch.from_numpy(self.ng.row(h)) for h in hists])[:, None, :]
-        return rows, self._state(hists)
+RefLMAdapter = NGramOracleLM   # LanguageModel duck type (ctc_beam_search.py:45-87): history rides in the cache tensor
 
 
 class Tok:
@@ -75,12 +51,18 @@ CASES = [  # name, T, V, beam, alpha, beta, thr, prune, seed, sharp
     ("v128_b3", 400, 128, 3, 0.4016, 1.625, -6, 3.221, 6, 6.0),
     ("v31_b5_flat", 80, 31, 5, 0.45, 1.53, -3, 3.17, 7, 1.5),
     ("v12_b10_pen", 120, 12, 10, 0.5, 0.2, -8, 5.0, 8, 2.5),
+    # BASELINE.json configs[2] shape (wav2vec2-like V=31+blank, beam 100, class-default LM weights) on a
+    # 2400-frame (48 s at 50 fps) stretch: the longest the pure-Python reference class finishes in minutes
+    ("cfg3_v31_b100_t2400", 2400, 31, 100, 0.45, 1.53, -6, 3.17, 9, 5.0),
 ]
 
 
 def main():
     out = {}
+    check_only = "--check-only" in sys.argv          # small cases only, nothing written
     for name, T, V, W, alpha, beta, thr, prune, seed, sharp in CASES:
+        if check_only and T > 400:
+            continue
         arpa = f"/tmp/beam_{name}.arpa"
         write_synthetic_arpa(arpa, V, order=4, counts=(None, 40 * V, 60 * V, 60 * V), seed=seed)
         order, grams = read_arpa(arpa)
@@ -96,6 +78,12 @@ def main():
         assert len(got) == len(orc), (name, len(got), len(orc))
         for g, o in zip(got, orc):
             assert np.float32(g[0]).tobytes() == np.float32(o[0]).tobytes() and g[1:] == o[1:], (name, g[:1], o[:1])
+        if T <= 400:                                  # the oracle's LanguageModel-protocol mode == the class, too
+            orc2 = BeamSearchOracle(V, W, lp, NGramOracleLM(ng), alpha=alpha, beta=beta, blank_id=V,
+                                    top_am_threshold=thr, prune_less_than_val=prune, lm_protocol=True, **pen
+                                    ).run_search().result()
+            assert [(np.float32(o[0]).tobytes(),) + tuple(o[1:]) for o in orc2] == \
+                   [(np.float32(g[0]).tobytes(),) + tuple(g[1:]) for g in got], name
         out[f"{name}_meta"] = np.array([T, V, W, alpha, beta, thr, -1.0 if prune is None else prune, seed, sharp,
                                         pen.get("blank_penalty", 0.0), pen.get("repitition_penalty", 0.0)])
         out[f"{name}_scores"] = np.array([g[0] for g in got], dtype=np.float32)
@@ -104,6 +92,9 @@ def main():
         out[f"{name}_stimes"] = np.array([t for g in got for t in g[2]], dtype=np.int64)
         out[f"{name}_blankend"] = np.array([g[3] for g in got], dtype=np.bool_)
         print(name, "beams", len(got), "best", got[0][0], "len", len(got[0][1]))
+    if check_only:
+        print("oracle (both LM modes) == reference on the small cases; nothing written")
+        return
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "beam_ref.npz"), **out)
     print("oracle == reference on all cases; wrote tests/golden/beam_ref.npz")
 

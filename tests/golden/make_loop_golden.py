@@ -113,6 +113,15 @@ def main():
         torch.manual_seed(77)
         res = ref_lib.cutout(spec, seq_len=512, cutout_val=mode, num_rectangles=40, max_width=60, max_height=12)
         out[f"cutout_{mode}"] = res[0].numpy().astype(np.float32)
+    # frame_shuffle (lib.py:81-84) and add_random_noise (:379-382): the reference functions under a fixed torch
+    # seed; the tests re-draw the permutations / the normal field with the same seed on the host
+    spec = toy_spec(4, 200).clone()
+    for td_, fd_ in ((True, False), (False, True), (True, True)):
+        torch.manual_seed(78)
+        res = ref_lib.frame_shuffle(spec.clone(), time_dimension=td_, freq_dimension=fd_)
+        out[f"frame_shuffle_t{int(td_)}f{int(fd_)}"] = res[0].numpy().astype(np.float32)
+    torch.manual_seed(79)
+    out["add_random_noise_0p3"] = ref_lib.add_random_noise(spec.clone(), 0.3)[0].numpy().astype(np.float32)
     # chunk index vectors from the reference's prepare_chunks at the BASELINE window settings
     for spec_n in (6000, 120000, 360000, 415990):
         td, keys = ref_lib.prepare_chunks(torch.zeros(1, 1, spec_n), 16384, 14336)

@@ -24,7 +24,7 @@ def test_header_symbols_exported():
 def test_binding_covers_header():
     import dae._C as C
     assert sorted(C._PROTOS) == _declared_symbols()
-    assert C.lib().dae_abi_version() == 1
+    assert C.lib().dae_abi_version() == 2
 
 
 def test_scratch_sizes_and_errors():

@@ -360,3 +360,51 @@ def test_cutout_matches_oracle(cuda, mode):
     cutout(view, 16384, cutout_val="zero", rects=rects)
     assert torch.equal(big[:, :, :1000], before[:, :, :1000]) and torch.equal(big[:, :, 4000:], before[:, :, 4000:])
     assert (view[0].cpu().numpy() == 0).sum() > 0
+
+
+# ---------------------------------------------------------------- frame shuffle / additive noise (f-3)
+@pytest.mark.parametrize("td,fd", [(True, False), (False, True), (True, True)])
+def test_frame_shuffle_matches_reference_golden(cuda, td, fd):
+    """Host-drawn permutations in the reference's order + the gather kernel == the reference's own frame_shuffle()
+    (golden), bit for bit; also against the oracle on a strided window view at the hot-path size."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from toy import toy_spec
+    from dae.augment import draw_frame_shuffle, frame_shuffle
+    from oracle import augment_extra_oracle as ax
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loop_toy.npz"))
+    spec = toy_spec(4, 200)
+    torch.manual_seed(78)
+    out = frame_shuffle(spec.to(cuda), time_dimension=td, freq_dimension=fd)
+    np.testing.assert_array_equal(out[0].cpu().numpy(), gold[f"frame_shuffle_t{int(td)}f{int(fd)}"])
+    g = torch.Generator().manual_seed(6)
+    big = torch.randn(1, 80, 20000, generator=g)
+    view = big.to(cuda)[:, :, 1500:1500 + 16384]
+    pt, pf = draw_frame_shuffle(80, 16384, td, fd, generator=g)
+    out = frame_shuffle(view, td, fd, perms=(pt, pf))
+    ref = ax.frame_shuffle(big[:, :, 1500:1500 + 16384].numpy(), None if pt is None else pt.numpy(),
+                           None if pf is None else pf.numpy())
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+
+
+def test_add_random_noise_matches_reference_golden(cuda):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from toy import toy_spec
+    from dae.augment import add_random_noise
+    from oracle import augment_extra_oracle as ax
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loop_toy.npz"))
+    spec = toy_spec(4, 200)
+    x = spec.to(cuda).clone()
+    torch.manual_seed(79)
+    out = add_random_noise(x, 0.3)                      # draws randn on the host like the reference's normal()
+    assert out.data_ptr() == x.data_ptr()
+    np.testing.assert_allclose(x[0].cpu().numpy(), gold["add_random_noise_0p3"], rtol=0, atol=5e-7)
+    g = torch.Generator().manual_seed(8)
+    big, z = torch.randn(1, 80, 16384, generator=g) * 2.5 + 0.7, torch.randn(1, 80, 16384, generator=g)
+    y = big.to(cuda).clone()
+    add_random_noise(y, 0.05, z=z)
+    np.testing.assert_allclose(y.cpu().numpy(), ax.add_random_noise(big.numpy(), z.numpy(), 0.05), rtol=0, atol=1e-6)
+    assert add_random_noise(y, 0) is y

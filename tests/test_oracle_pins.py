@@ -167,6 +167,43 @@ def test_cutout_oracle_matches_reference(mode):
     assert (out != spec).any()
 
 
+def _toy_gold():
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from toy import toy_spec
+    return toy_spec, np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loop_toy.npz"))
+
+
+@pytest.mark.parametrize("td,fd", [(True, False), (False, True), (True, True)])
+def test_frame_shuffle_oracle_matches_reference(td, fd):
+    """Permutation draw order (time, then frequency) + gather vs the reference's own frame_shuffle() (lib.py:81-84)."""
+    from dae.augment import draw_frame_shuffle
+    from oracle import augment_extra_oracle as ax
+    toy_spec, gold = _toy_gold()
+    spec = toy_spec(4, 200).numpy()
+    torch.manual_seed(78)
+    pt, pf = draw_frame_shuffle(80, 200, td, fd)
+    out = ax.frame_shuffle(spec, None if pt is None else pt.numpy(), None if pf is None else pf.numpy())
+    np.testing.assert_array_equal(out[0], gold[f"frame_shuffle_t{int(td)}f{int(fd)}"])
+
+
+def test_add_random_noise_oracle_matches_reference():
+    """normal(0, std, size) == randn(size) * std for the same generator state, and the restated std/scale/add vs
+    the reference's own add_random_noise() (lib.py:379-382)."""
+    from oracle import augment_extra_oracle as ax
+    toy_spec, gold = _toy_gold()
+    spec = toy_spec(4, 200)
+    torch.manual_seed(79)
+    a = torch.normal(0, std=spec.std(), size=spec.shape)
+    torch.manual_seed(79)
+    z = torch.randn(spec.shape)
+    assert torch.equal(a, z * spec.std())
+    out = ax.add_random_noise(spec.numpy(), z.numpy(), 0.3)
+    np.testing.assert_allclose(out[0], gold["add_random_noise_0p3"], rtol=0, atol=5e-7)
+    assert np.abs(out - spec.numpy()).max() > 0.1
+
+
 @pytest.mark.parametrize("T,C,L,K", [(37, 11, 9, 8), (16, 6, 7, 8), (8, 5, 0, 8), (5, 5, 2, 8), (20, 4, 9, 4), (19, 7, 5, 16)])
 def test_blocked_ctc_decomposition_equals_per_frame_recursion(T, C, L, K):
     """The time-blocked factorisation the GPU path uses (transfer bands, boundary scan in both directions, block

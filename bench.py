@@ -102,17 +102,21 @@ def run_reference(a, rank, world):
     from dae.optim import MADGRAD
     torch.set_num_threads(os.cpu_count() or 1)
     tok = standin.SyntheticTokenizer()
-    model = standin.build_model(tok.vocab_size(), device="cpu", seed=0)
+    on_gpu = a.ref_device == "cuda" and torch.cuda.is_available()
+    model = standin.build_model(tok.vocab_size(), device="cuda:0" if on_gpu else "cpu", seed=0)
     spec = torch.randn(1, 80, a.frames, generator=torch.Generator().manual_seed(1))
     model.set_spike_prior(2048, nonblank_frac=0.3, seed=0)
     args = make_args(standin.default_config())
-    sample_windows = 1
+    sample_windows = n_windows(a.frames) if on_gpu else 1     # the CPU arm times a bounded sample and extrapolates
     audio_h = a.frames / FPS / 3600.0 / n_windows(a.frames) * sample_windows
 
     def step():
         random.seed(0)
         torch.manual_seed(0)
-        dynamic_eval_reference(args, model, spec, SEQ_LEN, OVERLAP, tok, MADGRAD, max_windows=sample_windows)
+        dynamic_eval_reference(args, model, spec, SEQ_LEN, OVERLAP, tok, MADGRAD,
+                               max_windows=None if on_gpu else sample_windows)
+        if on_gpu:
+            torch.cuda.synchronize()
     for _ in range(a.warmup):
         step()
     t0 = time.perf_counter()
@@ -122,7 +126,9 @@ def run_reference(a, rank, world):
     val = audio_h * a.steps / dt
     cores = torch.get_num_threads()
     sample = (f"{sample_windows} of {n_windows(a.frames)} windows of a {a.frames}-frame recording per step "
-              f"(adapt step + final pass + stitch), model and CTC on the CPU")
+              f"(adapt step + final pass + stitch), " +
+              ("stand-in encoder and torch CTC on cuda:0, augmentation / greedy / stitch on the host (the reference's "
+               "own placement)" if on_gpu else "model and CTC on the CPU; value extrapolated linearly in windows"))
     print(json.dumps({
         "impl": "reference", "metric": "audio-hours/sec dynamic-eval", "value": val, "unit": "audio-hours/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
@@ -215,6 +221,148 @@ def aux_kernels(peak):
         {"frames_per_s": T / med, "audio_hours_per_s": T / 50 / 3600 / med, "lm_nodes": lm.n_nodes,
          "lm_hbm_bytes": lm.nbytes() + 8 * int((lm.depth < lm.order).sum()) * V})
     return out
+
+
+def ctc_table(peak, tm):
+    """CTC loss+grad at the adapt step's frame/class counts for N in {1, 8, 64, 256}: torch's CUDA
+    ctc_loss (what the reference calls on a GPU, lcasr/lib.py:492,575-579) beside dae's two implementations.
+    Labels = greedy of the posteriors themselves (teacher = student), L ~ 600 per sample."""
+    from dae import _C
+    from dae.ctc import CTCLoss
+    from dae.greedy import greedy_ids_device
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from kbench import peaky
+    g = torch.Generator(device="cuda").manual_seed(7)
+    T, Cc = 2048, 4096
+    out = {}
+    for N in (1, 8, 64, 256):
+        post = torch.stack([peaky(T, Cc, Cc - 1, g) for _ in range(N)], 1)      # [T,N,C]
+        labs = []
+        for n in range(N):
+            _, ids, k = greedy_ids_device(post[:, n], Cc - 1)
+            labs.append(ids[0, :int(k[0])].long())
+        Lmax = max(int(l.numel()) for l in labs)
+        tg = torch.zeros(N, Lmax, dtype=torch.long, device="cuda")
+        for n, l in enumerate(labs):
+            tg[n, :l.numel()] = l
+        tl = torch.tensor([int(l.numel()) for l in labs], device="cuda")
+        il = torch.full((N,), T, device="cuda")
+        x = post.requires_grad_()
+        nbytes = 2 * T * N * Cc * 4
+        row = {"shape": [T, N, Cc], "Lmax": Lmax, "algorithmic_bytes": nbytes}
+
+        def run(lossf):
+            def fb():
+                x.grad = None
+                (lossf(x, tg, il, tl) / (T * N)).backward()
+            med, _ = tm.time(fb, 5 if N >= 64 else 10)
+            return {"ms": med * 1e3, "gbs": nbytes / med / 1e9, "frac_of_hbm_peak": nbytes / med / 1e9 / peak}
+        row["torch_cuda_ctc_loss"] = run(torch.nn.CTCLoss(blank=Cc - 1, reduction="sum"))
+        dae_f = CTCLoss(blank=Cc - 1, reduction="sum", validate=False)
+        try:
+            _C.ctc_configure(blocked=0)
+            row["dae_chain"] = run(dae_f)
+            if N <= 8:
+                _C.ctc_configure(blocked=1)
+                row["dae_time_blocked"] = run(dae_f)
+        finally:
+            _C.ctc_configure()
+        row["dae_default"] = "time_blocked" if N <= 8 else "chain"
+        best = min(row[k]["ms"] for k in ("dae_chain", "dae_time_blocked") if k in row)
+        row["speedup_vs_torch_cuda"] = row["torch_cuda_ctc_loss"]["ms"] / best
+        out[f"N={N}"] = row
+        del post, x, tg
+        torch.cuda.empty_cache()
+    return out
+
+
+def numba_softdtw_table(tm):
+    """The reference's numba-CUDA soft-DTW algorithm (one block per sample, max(N,M) <= 1024 threads, global-memory
+    operands, fp64 math: lcasr_nemo/soft_dtw_cuda.py:33-111) restated in oracle/softdtw_numba_port.py and timed on
+    this GPU beside dae at the reference's profile() shapes (:382-428) and at its 1024 cap."""
+    from dae.soft_dtw_cuda import softdtw_backward, softdtw_forward
+    out = {}
+    try:
+        from oracle import softdtw_numba_port as nb
+        nb_err = None
+    except Exception as e:                                      # numba missing / cannot target this GPU
+        nb, nb_err = None, f"{type(e).__name__}: {e}"
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    for (B, N, M) in ((128, 17, 15), (512, 64, 64), (512, 256, 256), (8, 1024, 1024)):
+        a_, b_ = torch.rand(B, N, 2, generator=g, device="cuda"), torch.rand(B, M, 2, generator=g, device="cuda")
+        D = ((a_[:, :, None, :] - b_[:, None, :, :]) ** 2).sum(-1).contiguous()
+        row = {}
+        fw, _ = tm.time(lambda: softdtw_forward(D, 1.0, 0.0), 10)
+        _, W, _ = softdtw_forward(D, 1.0, 0.0)
+        go = torch.ones(B, device="cuda")
+        bw, _ = tm.time(lambda: softdtw_backward(W, go), 10)
+        row["dae_fwd_ms"], row["dae_bwd_ms"] = fw * 1e3, bw * 1e3
+        if nb is not None:
+            try:
+                f2, b2 = nb.time_fwd_bwd(D, 1.0, 0.0, tm)
+                row["numba_cuda_fwd_ms"], row["numba_cuda_bwd_ms"] = f2 * 1e3, b2 * 1e3
+                row["speedup_fwd_bwd"] = (f2 + b2) / (fw + bw)
+            except Exception as e:
+                row["numba_cuda_error"] = f"{type(e).__name__}: {str(e)[:200]}"
+        else:
+            row["numba_cuda_error"] = nb_err
+        out[f"[{B},{N},{M}]"] = row
+    return out
+
+
+def gpu_reference_loop(frames, dev, windows=None):
+    """The reference's real device placement (lcasr/lib.py:538-629): encoder + torch CTC on the GPU, SpecAugment on
+    the CPU, H2D of every [2,80,16384] batch, D2H of the posteriors for greedy decoding, CPU overlap stitch —
+    through oracle/ref_loop.py on the same stand-in model, one recording, wall clock."""
+    import random
+    from oracle.ref_loop import dynamic_eval_reference
+    from dae import standin
+    from dae.optim import MADGRAD
+    tok = standin.SyntheticTokenizer()
+    model = standin.build_model(tok.vocab_size(), device=dev, seed=0)
+    model.set_spike_prior(2048, nonblank_frac=0.3, seed=0)
+    spec = torch.randn(1, 80, frames, generator=torch.Generator().manual_seed(100))
+    args = make_args(standin.default_config())
+    nw = n_windows(frames)
+    k = nw if windows is None else min(windows, nw)
+
+    def once():
+        random.seed(0)
+        torch.manual_seed(0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dynamic_eval_reference(args, model, spec, SEQ_LEN, OVERLAP, tok, MADGRAD, max_windows=None if k == nw else k)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+    once() if k < nw else None                                 # warm-up (cuDNN/cuBLAS plans) on the bounded form only
+    dt = once()
+    audio_h = frames / FPS / 3600.0 * k / nw
+    return {"value": audio_h / dt, "unit": "audio-hours/s", "seconds": dt, "windows": k, "of_windows": nw,
+            "cores": torch.get_num_threads(),
+            "what": "reference loop restated (oracle/ref_loop.py): stand-in encoder + torch.nn.CTCLoss on the GPU, "
+                    "CPU SpecAugment, per-step H2D of the batch and D2H of [2048,4096] posteriors for greedy, CPU stitch"}
+
+
+def awmc_throughput(frames, dev, tok, model):
+    """lib.AWMC (lcasr/lib.py:206-376; published RTF 0.097, timeit_earnings22.sh:10-12) on one recording."""
+    import random
+    from dae import lib
+    from dae.optim import MADGRAD
+    spec = torch.randn(1, 80, frames, generator=torch.Generator().manual_seed(100)).to(dev)
+    args = make_args(__import__("dae.standin", fromlist=["x"]).default_config())
+
+    def once():
+        random.seed(0)
+        torch.manual_seed(0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ids = lib.AWMC(args, model, spec, SEQ_LEN, OVERLAP, tok, use_tqdm=False, optim=MADGRAD, output="greedy")
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, len(ids)
+    dt, n = once()
+    dt, n = once()
+    return {"value": frames / FPS / 3600.0 / dt, "unit": "audio-hours/s", "seconds": dt, "rtf": dt / (frames / FPS),
+            "hyp_ids": n, "what": "dae.lib.AWMC, 1 epoch, same recording/model/SpecAugment as the headline"}
 
 
 def run_dae(a, rank, world, local):
@@ -315,6 +463,18 @@ def run_dae(a, rank, world, local):
                 "note": "N=1: time-blocked lattice (transfer bands + 256-step boundary scan + fused block gradient); the scan is a dependent chain (latency-bound); see DESIGN.md"}
     cpu = cpu_baseline_sample(a.frames) if world == 1 else None
     aux = aux_kernels(peak) if (world == 1 and not a.no_aux) else None
+    extra = {}
+    if world == 1 and not a.no_aux:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from kbench import Timer
+        tm = Timer()
+        extra["ctc_vs_torch_cuda"] = ctc_table(peak, tm)
+        extra["softdtw_vs_numba_cuda"] = numba_softdtw_table(tm)
+        del tm
+        torch.cuda.empty_cache()
+        extra["awmc"] = awmc_throughput(a.frames, dev, tok, model)
+        extra["gpu_reference_loop"] = gpu_reference_loop(a.frames, dev)
+        extra["gpu_reference_loop"]["dae_speedup_e2e"] = e2e / extra["gpu_reference_loop"]["value"]
     line = {
         "metric": "audio-hours/sec dynamic-eval", "value": value, "unit": "audio-hours/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": t_dev / a.steps * 1e3, "higher_is_better": True,
@@ -324,10 +484,106 @@ def run_dae(a, rank, world, local):
         "e2e": {"value": e2e, "unit": "audio-hours/s", "h2d_bytes_per_step": int(h2d_step),
                 "d2h_bytes_per_step": int(d2h_step), "ms_per_step": t_e2e / a.steps * 1e3},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": table, "cpu_baseline": cpu,
-        "kernels_at_baseline_shapes": aux,
+        "kernels_at_baseline_shapes": aux, **extra,
         "avg_pseudo_label_len": (sum(label_lens) / len(label_lens)) if label_lens else None,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_sweep(a, rank, world, local):
+    """BASELINE.json configs[4]: a FIXED ragged set of synthetic recordings (TED-LIUM-, Rev16- or Earnings22-shaped,
+    SURVEY.md §8d cfg5) LPT-sharded over the ranks by frame count: strong scaling.  One step = the whole sweep.
+    Prints the all-reduced (S, D, I, words, n) and a hash of all hypotheses so lines at different N can be compared
+    for bit-equal WER; the limiter is named from the per-rank busy times."""
+    import hashlib
+    import random
+    import zlib
+    import torch.distributed as dist
+    from dae import _C, lib, standin
+    from dae.optim import MADGRAD
+    from dae.shard import all_reduce_counts, gather_objects, lpt_assign
+    from dae.wer import rates_from_counts, word_error_counts
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    _C.lib()
+    tok = standin.SyntheticTokenizer()
+    model = standin.build_model(tok.vocab_size(), device=dev, seed=0)
+    model.set_spike_prior(2048, nonblank_frac=0.3, seed=0)
+    args = make_args(standin.default_config())
+    recs = standin.synthetic_recordings(a.sweep, tokenizer=tok, scale=a.sweep_scale)
+    frames = [r["frames"] for r in recs]
+    mine = lpt_assign(frames, world)[rank]
+    specs = {i: recs[i]["process_fn"](recs[i])[0].pin_memory() for i in mine}        # host spectrograms (pinned)
+    audio_h = sum(frames) / FPS / 3600.0
+
+    def sweep():
+        hyp, t_busy = {}, 0.0
+        for i in mine:
+            key = zlib.crc32(f"0|0|{recs[i]['id']}".encode())                        # seeded per recording, not per rank
+            random.seed(key)
+            torch.manual_seed(key ^ 0x5bd1e995)
+            t0 = time.perf_counter()
+            hyp[i] = lib.dynamic_eval(args, model, specs[i], SEQ_LEN, OVERLAP, tok, use_tqdm=False, optim=MADGRAD,
+                                      output="greedy")
+            t_busy += time.perf_counter() - t0
+        counts = word_error_counts([tok.decode(hyp[i]) for i in mine], [recs[i]["text"] for i in mine])
+        total = all_reduce_counts(counts, dev)
+        return hyp, total, t_busy
+
+    def timed(n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            out = sweep()
+        e.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([s.elapsed_time(e) * 1e-3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+    # warm-up: W passes over this rank's SHORTEST recording (plans, allocator), not the whole sweep
+    if mine:
+        j = min(mine, key=lambda i: frames[i])
+        for _ in range(a.warmup):
+            lib.dynamic_eval(args, model, specs[j], SEQ_LEN, OVERLAP, tok, use_tqdm=False, optim=MADGRAD, output="greedy")
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _C.launch_count()
+    t, (hyp, total, busy) = timed(a.steps)
+    launches = _C.launch_count() - l0
+    clocks = sampler.stop()
+    parts = gather_objects((hyp, busy / 1.0, [frames[i] for i in mine]))
+    if rank != 0:
+        return
+    all_h = {}
+    for h, _, _ in parts:
+        all_h.update(h)
+    digest = hashlib.sha256(repr([(i, all_h[i]) for i in sorted(all_h)]).encode()).hexdigest()[:16]
+    wer, words, ir, dr, sr = rates_from_counts(total)
+    busy_s = [b for _, b, _ in parts]
+    load = [sum(f) for _, _, f in parts]
+    longest = max(frames)
+    lim = ("LPT imbalance: the busiest rank holds %.1f%% of the frames vs %.1f%% ideal; the longest recording alone is %.1f%%"
+           % (100 * max(load) / sum(frames), 100 / world, 100 * longest / sum(frames)))
+    print(json.dumps({
+        "metric": "audio-hours/sec dynamic-eval", "value": audio_h * a.steps / t, "unit": "audio-hours/s",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": t / a.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"sweep over {len(recs)} {a.sweep}-shaped synthetic recordings "
+                               f"({audio_h:.2f} audio hours, {min(frames)}-{max(frames)} frames), LPT-sharded by frames",
+                   "sweep_scale": a.sweep_scale, "parallelism": f"{world} rank(s), one int64[5] all-reduce per sweep",
+                   "l2": "inputs larger than L2"},
+        "wer_counts_SDIWn": [int(x) for x in total.tolist()], "wer": wer, "hypotheses_sha256_16": digest,
+        "per_rank_busy_s": busy_s, "per_rank_frames": load, "limiter": lim, "gpu_launches": int(launches),
+        "e2e": {"value": audio_h * a.steps / t, "unit": "audio-hours/s",
+                "h2d_bytes_per_step": int(sum(frames) * 80 * 4), "d2h_bytes_per_step": int(sum(4 * len(v) + 4 for v in all_h.values())),
+                "note": "sweep inputs start in pinned host memory: value == e2e"},
+        "clocks": clocks}), flush=True)
 
 
 def main():
@@ -338,12 +594,24 @@ def main():
     ap.add_argument("--impl", default="dae", choices=["dae", "reference"])
     ap.add_argument("--frames", type=int, default=120000, help="frames per synthetic recording (100 fps)")
     ap.add_argument("--no-aux", dest="no_aux", action="store_true", help="skip the BASELINE-shape kernel table")
+    ap.add_argument("--sweep", default="", choices=["", "tedlium", "rev16", "earnings22"],
+                    help="strong-scaling sweep over a fixed ragged recording set (BASELINE.json configs[4])")
+    ap.add_argument("--sweep-scale", dest="sweep_scale", type=float, default=1.0, help="shrink the sweep's durations")
+    ap.add_argument("--ref-device", dest="ref_device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference: where the stand-in encoder + torch CTC run (cpu = host cores, the "
+                         "contract's arm; cuda = the reference's real placement, lcasr/lib.py:549)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return
     from dae.shard import init_distributed
     rank, world, local = init_distributed()
+    if a.sweep:
+        run_sweep(a, rank, world, local)
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
     if world != a.gpus and rank == 0:
         print(f"[bench] note: --gpus {a.gpus} but WORLD_SIZE={world}; launch N>1 with torch.distributed.run",
               file=sys.stderr)

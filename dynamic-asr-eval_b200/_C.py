@@ -35,6 +35,7 @@ _PROTOS = {
     "dae_noise_scratch_bytes": (c_size_t, []),
     "dae_add_noise": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, ctypes.c_float, c_void_p, c_size_t,
                               c_void_p, c_void_p]),
+    "dae_ctc_configure": (None, [c_int, c_int, c_int]),
     "dae_ctc_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dae_ctc_lattice": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
                                 c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -96,6 +97,11 @@ def stream_ptr(device=None):
 def require_cuda(t: torch.Tensor, name: str):
     if not t.is_cuda:
         raise DaeError(f"{name} must be a CUDA tensor: the dae kernels have no CPU path")
+
+
+def ctc_configure(blocked: int = -1, cluster: int = 0, pairs: int = 0):
+    """Force the CTC lattice implementation (tests / tools): see dae_ctc_configure in include/dae.h."""
+    lib().dae_ctc_configure(int(blocked), int(cluster), int(pairs))
 
 
 def launch_count() -> int:

@@ -60,8 +60,7 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
 }
 
 // Raise a kernel's dynamic shared-memory limit, once per (kernel, device, size): the driver call costs a few
-// microseconds of host time, which shows when the GPU is waiting for the launch.  (Not thread-safe beyond benign
-// double-setting: the table only ever grows and a lost update costs one more driver call.)
+// microseconds of host time, which shows when the GPU is waiting for the launch.  The cache is guarded by a mutex.
 cudaError_t ensure_dyn_smem_impl(const void* kern, int bytes);
 template <typename Kern>
 inline cudaError_t ensure_dyn_smem(Kern kern, int bytes) {

@@ -1179,8 +1179,7 @@ int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, i
   {
     // clusters of up to 8 regions hand over through DSMEM when the per-step mailbox fits in shared memory
     const size_t mbox_bytes = (size_t)(sc.nblk + 1) * kHaloWords * sizeof(int2);
-    const char* env = getenv("DAE_CTC_CLUSTER");
-    int cl = env ? atoi(env) : 8;
+    int cl = ctc_config().cluster.load(std::memory_order_relaxed);
     if (cl < 1 || cl > 8 || (cl & (cl - 1))) cl = 8;
     if (mbox_bytes > 96 * 1024 || sc.G < 2) cl = 1;
     while (cl > sc.G) cl >>= 1;

@@ -40,20 +40,24 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 // Thread geometry of the lattice kernel: P state pairs per consumer thread, NTc consumer threads.
 // Every consumer thread owns real or dummy pairs, so lattice rows are 2*NTc*P floats wide.
+// Path overrides (dae_ctc_configure): process-wide, read with relaxed atomics on every call; the environment
+// variables DAE_CTC_BLOCKED / DAE_CTC_CLUSTER / DAE_CTC_PAIRS only seed them once, when the library is first used.
+struct CtcConfig { std::atomic<int> blocked{-1}, cluster{0}, pairs{0}; };
+CtcConfig& ctc_config();
+
 static inline void lat_geometry(int Lmax, int& P, int& NTc) {
   constexpr int kMaxConsumers = kLatThreads - 64;        // two helper warps: centring + TMA
   const int pairs = Lmax + 1;
   P = (pairs + kMaxConsumers - 1) / kMaxConsumers;
   P = P <= 1 ? 1 : (P <= 2 ? 2 : 4);
-  static const int forced = [] { const char* e = getenv("DAE_CTC_PAIRS"); return e ? atoi(e) : 0; }();
+  const int forced = ctc_config().pairs.load(std::memory_order_relaxed);
   if ((forced == 1 || forced == 2 || forced == 4) && (pairs + forced - 1) / forced <= kMaxConsumers) P = forced;
   NTc = (((pairs + P - 1) / P + 31) / 32) * 32;
 }
 
 // The time-blocked path pays off when the per-frame chain would leave the GPU idle (few samples, many frames).
 static inline bool blocked_eligible(int T, int N, int Lmax) {
-  const char* env = getenv("DAE_CTC_BLOCKED");           // 0 = never, 1 = whenever it fits (tests drive both paths)
-  const int forced = env ? atoi(env) : -1;
+  const int forced = ctc_config().blocked.load(std::memory_order_relaxed);   // 0 = never, 1 = whenever it fits
   if (forced == 0) return false;
   const int nblk = (T + kBlkK - 1) / kBlkK;
   const size_t Sq = align_up((size_t)2 * Lmax + 1, kRegion);

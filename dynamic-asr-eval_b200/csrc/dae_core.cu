@@ -1,5 +1,8 @@
 // Library-level entry points of libdae.so: ABI version, error strings, launch counter.
+#include <cstdlib>
+#include <mutex>
 #include "common.cuh"
+#include "ctc_shared.cuh"
 
 namespace dae {
 std::atomic<int64_t> g_launches{0};
@@ -8,6 +11,13 @@ std::atomic<int64_t> g_launches{0};
 extern "C" int dae_abi_version(void) { return DAE_ABI_VERSION; }
 
 extern "C" int64_t dae_launch_count(void) { return dae::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" void dae_ctc_configure(int blocked, int cluster, int pairs) {
+  dae::CtcConfig& c = dae::ctc_config();
+  c.blocked.store(blocked < 0 ? -1 : (blocked ? 1 : 0));
+  c.cluster.store(cluster);
+  c.pairs.store(pairs);
+}
 
 extern "C" const char* dae_error_string(int code) {
   switch (code) {
@@ -23,10 +33,24 @@ extern "C" const char* dae_error_string(int code) {
 }
 
 namespace dae {
+CtcConfig& ctc_config() {
+  static CtcConfig cfg;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    cfg.blocked.store(env_int("DAE_CTC_BLOCKED", -1));
+    cfg.cluster.store(env_int("DAE_CTC_CLUSTER", 0));
+    cfg.pairs.store(env_int("DAE_CTC_PAIRS", 0));
+  });
+  return cfg;
+}
+
 cudaError_t ensure_dyn_smem_impl(const void* kern, int bytes) {
   struct Entry { const void* kern; int dev; int bytes; };
   static Entry table[128];
   static int used = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;

@@ -13,7 +13,7 @@ from . import _C, prof
 
 class _CTCFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, log_probs, targets, input_lengths, target_lengths, blank):
+    def forward(ctx, log_probs, targets, input_lengths, target_lengths, blank, validate=True):
         _C.require_cuda(log_probs, "log_probs")
         if log_probs.dtype != torch.float32:
             raise _C.DaeError("dae.CTCLoss computes in fp32; got " + str(log_probs.dtype))
@@ -44,6 +44,12 @@ class _CTCFunction(torch.autograd.Function):
         if tg.stride(1) != 1:
             tg = tg.contiguous()
         Lmax = int(tg.shape[1])
+        if validate and Lmax:
+            # torch raises on labels outside [0, C); the kernels index class rows with the raw label, so check on
+            # the device without a host sync (the error surfaces at the next synchronisation point)
+            used = torch.arange(Lmax, device=dev)[None, :] < tg_len[:, None]
+            torch._assert_async((((tg >= 0) & (tg < C)) | ~used).all(),
+                                "dae.CTCLoss: a target label lies outside [0, num_classes)")
         lib = _C.lib()
         nbytes = lib.dae_ctc_scratch_bytes(T, N, Lmax)
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -79,15 +85,17 @@ class _CTCFunction(torch.autograd.Function):
                                        nll.data_ptr(), g.data_ptr(), g_stride, grad.data_ptr(),
                                        scratch.data_ptr(), scratch.numel(), _C.stream_ptr(lp.device))
         _C.check(rc, "dae_ctc_grad")
-        return (grad[:, 0] if unbatched else grad), None, None, None, None
+        return (grad[:, 0] if unbatched else grad), None, None, None, None, None
 
 
-def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reduction="mean", zero_infinity=False):
-    """Functional form, same argument meaning as ``torch.nn.functional.ctc_loss``."""
+def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reduction="mean", zero_infinity=False,
+             validate=True):
+    """Functional form, same argument meaning as ``torch.nn.functional.ctc_loss``.  ``validate=False`` skips the
+    device-side label range check (the adapt loop's labels come straight from the tokenizer)."""
     if zero_infinity:
         raise _C.DaeError("zero_infinity=True is not used by the reference (SURVEY.md appendix A) and is not implemented")
     unbatched = log_probs.dim() == 2
-    nll = _CTCFunction.apply(log_probs, targets, input_lengths, target_lengths, blank)
+    nll = _CTCFunction.apply(log_probs, targets, input_lengths, target_lengths, blank, validate)
     if reduction == "sum":
         return nll.sum()
     if reduction == "none":
@@ -101,10 +109,10 @@ def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reducti
 class CTCLoss(torch.nn.Module):
     """``torch.nn.CTCLoss`` call signature (lcasr/lib.py:492) on the dae CUDA kernels."""
 
-    def __init__(self, blank: int = 0, reduction: str = "mean", zero_infinity: bool = False):
+    def __init__(self, blank: int = 0, reduction: str = "mean", zero_infinity: bool = False, validate: bool = True):
         super().__init__()
-        self.blank, self.reduction, self.zero_infinity = blank, reduction, zero_infinity
+        self.blank, self.reduction, self.zero_infinity, self.validate = blank, reduction, zero_infinity, validate
 
     def forward(self, log_probs, targets, input_lengths, target_lengths):
         return ctc_loss(log_probs, targets, input_lengths, target_lengths, self.blank, self.reduction,
-                        self.zero_infinity)
+                        self.zero_infinity, self.validate)

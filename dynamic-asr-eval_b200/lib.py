@@ -92,9 +92,35 @@ def prepare_chunks(spec, seq_len, overlap):
 # randomness in the reference's order, gather / streaming kernels on the device.
 
 
-def _freeze(model, args):
-    """lcasr/lib.py:163-204 (the three CLI freeze switches)."""
+def bitfit(model):
+    """lcasr/lib.py:148-160: train biases only (LayerNorm, Linear and batch-renorm biases)."""
+    for param in model.parameters():
+        param.requires_grad = False
+    for module in model.modules():
+        is_norm = isinstance(module, torch.nn.LayerNorm) or type(module).__name__ in ('FusedLayerNorm', 'BatchRenorm1d')
+        if (is_norm or isinstance(module, torch.nn.Linear)) and getattr(module, 'bias', None) is not None:
+            module.bias.requires_grad = True
+    return model
+
+
+def lm_path_from_paths():
+    """``lib.paths.checkpoints.lm`` of the reference (lcasr/lib.py:5, run_dynamic_eval_full.py:58): read from the
+    YAML file named by $DAE_PATHS (default ./paths.yaml) if it exists; None otherwise."""
+    import os
+    p = os.environ.get('DAE_PATHS', 'paths.yaml')
+    if not os.path.exists(p):
+        return None
+    import yaml
+    with open(p) as f:
+        cfg = yaml.safe_load(f) or {}
+    return (cfg.get('checkpoints') or {}).get('lm')
+
+
+def _freeze(model, args, allow_bitfit=False):
+    """lcasr/lib.py:163-204 (the three CLI freeze switches); AWMC also honours ``bitfit`` (:233-234)."""
     d = args.__dict__
+    if allow_bitfit and d.get('bitfit', False):
+        model = bitfit(model)
     if d.get('freeze_subsampling', False):
         for p in model.subsampling.parameters():
             p.requires_grad = False
@@ -180,7 +206,7 @@ def dynamic_eval_ctc_loss(
     model = _freeze(model, args)
 
     blank = model.decoder.num_classes - 1
-    ctc_loss_fn = CTCLoss(blank=blank, reduction='sum')
+    ctc_loss_fn = CTCLoss(blank=blank, reduction='sum', validate=False)   # labels come from tokenizer.encode
     optimizer = optim([p for p in model.parameters() if p.requires_grad], **lr_args)
     if optimizer_state is not None:
         optimizer.load_state_dict(optimizer_state)
@@ -414,7 +440,7 @@ def AWMC(
     params = list(model.parameters())
     original = [p.detach().clone() for p in params]
     req_grad = [p.requires_grad for p in params]
-    model = _freeze(model, args)
+    model = _freeze(model, args, allow_bitfit=True)
     model.train()                                           # lib.py:242
     ema_leader = _EMA(model.parameters(), decay=d.get('ema_decay', 0.999))
     ema_leader.update()

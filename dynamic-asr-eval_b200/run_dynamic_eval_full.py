@@ -50,6 +50,21 @@ def main(args, model=None, tokenizer=None, data=None, normalize=None, beamsearch
     normalize = normalize or _default_normalize()
     blank = model.decoder.num_classes - 1
     decoder = GreedyCTCDecoder(tokenizer=tokenizer, blank_id=blank)
+    if args.__dict__.get('beamsearch', False) and beamsearch is None:
+        # run_dynamic_eval_full.py:56-64: the reference reads the LM checkpoint path from paths.yaml
+        # (lib.paths.checkpoints.lm); here it is an ARPA file named by `-kwargs lm_path=...` or lib.paths
+        lm_path = args.__dict__.get('lm_path', None) or lib.lm_path_from_paths()
+        if not lm_path:
+            raise ValueError("-beamsearch needs an ARPA language model: pass `-kwargs lm_path=/path/to/lm.arpa[.gz]` "
+                             "or set checkpoints.lm in paths.yaml (DAE_PATHS)")
+        beamsearch = lib.load_beamsearch(
+            path=lm_path,
+            alpha=args.__dict__.get('lm_alpha', 0.45),
+            beta=args.__dict__.get('lm_beta', 1.53),
+            prune_less_than_val=args.__dict__.get('lm_prune_less_than_val', 3.17),
+            top_am_threshold=args.__dict__.get('lm_top_am_threshold', -6),
+            tokenizer=tokenizer,
+        )
     beams = args.__dict__.get('lm_eval_beams', 20)
     if args.awmc:
         eval_fn = lib.AWMC

@@ -16,7 +16,8 @@
  *     as void*, NULL = legacy default stream);
  *   - return value: 0 = enqueued, < 0 = argument error (DAE_E_*), > 0 = a cudaError_t;
  *   - strides are in ELEMENTS, not bytes; the innermost (class / column) stride is 1;
- *   - no global state: re-entrant from several host threads on distinct streams.
+ *   - re-entrant from several host threads on distinct streams.  Process-wide state is limited to the launch
+ *     counter, a mutex-guarded cache of per-kernel shared-memory attributes, and the CTC path override below.
  */
 #ifndef DAE_H_
 #define DAE_H_
@@ -141,6 +142,13 @@ int dae_ctc_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C,
                  const int64_t* in_len, const int64_t* tgt_len, int blank,
                  const float* nll, const float* gout, int64_t gout_stride,
                  float* grad, const void* scratch, size_t scratch_bytes, void* stream);
+
+/* Debug/test switch for which CTC lattice implementation dae_ctc_lattice and dae_ctc_scratch_bytes pick
+ * (process-wide; seeded once from the environment variables DAE_CTC_BLOCKED / DAE_CTC_CLUSTER / DAE_CTC_PAIRS):
+ *   blocked  -1 = by shape (default), 0 = always the per-frame chain, 1 = the time-blocked scan whenever it fits
+ *   cluster  thread-block cluster size of the scan's region hand-over (1, 2, 4, 8; 0 = default 8; 1 = global memory only)
+ *   pairs    state pairs per consumer thread of the per-frame chain (1, 2, 4; 0 = by label length) */
+void dae_ctc_configure(int blocked, int cluster, int pairs);
 
 /* ------------------------------------------------------------------------------------
  * (f-1) overlap-average stitch of window posteriors, with a fused greedy argmax.

@@ -40,23 +40,28 @@ def test_scratch_sizes_and_errors():
     assert lib.dae_ctc_lattice(None, 0, 0, 1, 1, 1, None, 0, 0, None, None, 0, None, None, 0, None) == -1
 
 
-def test_ctc_scratch_covers_both_lattice_paths(monkeypatch):
+def test_ctc_scratch_covers_both_lattice_paths():
     """dae_ctc_scratch_bytes follows the path dae_ctc_lattice would take for the shape: the time-blocked path
     (few samples, many frames) needs the band / boundary / emission arrays on top of the chain path's rows."""
     import dae._C as C
     lib = C.lib()
-    monkeypatch.setenv("DAE_CTC_BLOCKED", "0")
-    chain = lib.dae_ctc_scratch_bytes(2048, 1, 600)
-    monkeypatch.setenv("DAE_CTC_BLOCKED", "1")
-    blocked = lib.dae_ctc_scratch_bytes(2048, 1, 600)
-    monkeypatch.delenv("DAE_CTC_BLOCKED")
+    try:
+        C.ctc_configure(blocked=0)
+        chain = lib.dae_ctc_scratch_bytes(2048, 1, 600)
+        C.ctc_configure(blocked=1)
+        blocked = lib.dae_ctc_scratch_bytes(2048, 1, 600)
+    finally:
+        C.ctc_configure()
     default = lib.dae_ctc_scratch_bytes(2048, 1, 600)
     assert chain > 0 and blocked > chain + 20 * 2 ** 20 and default == blocked      # the adapt step takes the blocked path
     # large batches and band arrays beyond 256 MB stay on the chain path
     assert lib.dae_ctc_scratch_bytes(2048, 64, 600) < 64 * blocked
     big_t = lib.dae_ctc_scratch_bytes(200000, 1, 4000)
-    monkeypatch.setenv("DAE_CTC_BLOCKED", "0")
-    assert lib.dae_ctc_scratch_bytes(200000, 1, 4000) == big_t
+    try:
+        C.ctc_configure(blocked=0)
+        assert lib.dae_ctc_scratch_bytes(200000, 1, 4000) == big_t
+    finally:
+        C.ctc_configure()
 
 
 def test_no_cpu_fallback():

@@ -205,7 +205,7 @@ def test_cuda_hot_path_vocab_walks_the_trie(cuda, tmp_path):
     assert lm.dense_tables(cuda) == (None, None)
     ng = NGramOracle(grams, order, V)
     for W, T, seed in ((3, 160, 41), (20, 60, 42)):
-        lp = peaky_log_probs(T, V + 1, V, seed, sharp=6.0)
+        lp = peaky_log_probs(T, V + 1, V, seed, sharp=12.0)
         kw = dict(alpha=0.45, beta=1.53, blank_id=V, top_am_threshold=-6, prune_less_than_val=3.17)
         bs = BeamSearch(_Tok(V), W, torch.from_numpy(lp).to(cuda), lm, **kw)
         bs.run_search(use_tqdm=False)

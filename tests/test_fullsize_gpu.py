@@ -63,7 +63,14 @@ def test_ctc_batch_of_64_properties(cuda):
     assert x.grad[:1500, 3].abs().sum() > 0
 
 
-def test_ctc_adapt_step_blocked_equals_chain(cuda, monkeypatch):
+@pytest.fixture
+def C_():
+    import dae._C as C
+    yield C
+    C.ctc_configure()
+
+
+def test_ctc_adapt_step_blocked_equals_chain(cuda, C_):
     """The adapt step's shape ([2048, N, 4096], N = 1 and a ragged N = 2 as in AWMC): the time-blocked lattice
     (default for few samples) and the per-frame chain are two implementations of the same function: losses agree
     to 1e-6 relative, gradients within the 1e-4 elementwise tolerance, gradient rows sum to zero, padding frames are zero."""
@@ -84,7 +91,7 @@ def test_ctc_adapt_step_blocked_equals_chain(cuda, monkeypatch):
         tl = torch.tensor([int(l.numel()) for l in labs], device="cuda")
         out = {}
         for path in ("0", "1"):
-            monkeypatch.setenv("DAE_CTC_BLOCKED", path)
+            C_.ctc_configure(blocked=int(path))
             x = post.clone().requires_grad_()
             nll = ctc_loss(x, tg, il, tl, blank=C - 1, reduction="none")
             (nll.sum() / T).backward()

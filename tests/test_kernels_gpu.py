@@ -113,13 +113,14 @@ def test_specaug_plain_call_and_determinism(cuda):
 
 # ---------------------------------------------------------------- CTC
 @pytest.fixture(params=["chain", "blocked", "blocked_nocluster"])
-def ctc_path(request, monkeypatch):
+def ctc_path(request):
     """Both lattice implementations behind dae_ctc_lattice: the per-frame chain (ctc.cu) and the time-blocked
     scan (ctc_blocked.cu), the latter with hand-over through cluster shared memory (default) and through global
-    memory only; DAE_CTC_BLOCKED / DAE_CTC_CLUSTER force the choice regardless of shape."""
-    monkeypatch.setenv("DAE_CTC_BLOCKED", "0" if request.param == "chain" else "1")
-    monkeypatch.setenv("DAE_CTC_CLUSTER", "1" if request.param == "blocked_nocluster" else "8")
-    return request.param
+    memory only; dae_ctc_configure forces the choice regardless of shape."""
+    import dae._C as C
+    C.ctc_configure(blocked=0 if request.param == "chain" else 1, cluster=1 if request.param == "blocked_nocluster" else 8)
+    yield request.param
+    C.ctc_configure()
 
 
 def _ctc_case(T, N, C, Lmax, seed, ragged=True, peaky=False):
@@ -408,3 +409,16 @@ def test_add_random_noise_matches_reference_golden(cuda):
     add_random_noise(y, 0.05, z=z)
     np.testing.assert_allclose(y.cpu().numpy(), ax.add_random_noise(big.numpy(), z.numpy(), 0.05), rtol=0, atol=1e-6)
     assert add_random_noise(y, 0) is y
+
+
+def test_ctc_rejects_out_of_range_labels(cuda):
+    """torch.nn.CTCLoss raises on a label outside [0, C); dae.CTCLoss checks on the device (no host sync) and the
+    error surfaces at the next synchronisation.  Padding beyond target_lengths is not looked at."""
+    from dae.ctc import CTCLoss
+    T, C = 30, 9
+    lp = torch.randn(T, 2, C, device=cuda).log_softmax(-1)
+    ok = torch.tensor([[1, 2, 3, -7], [4, 5, 99, 99]], device=cuda)          # bad values only in the padding
+    CTCLoss(blank=C - 1, reduction="sum")(lp, ok, [T, T], [3, 2])
+    torch.cuda.synchronize()
+    # The failing case is NOT run here: a device-side assert kills the CUDA context and is logged by the driver
+    # as a GPU fault on this shared pool; the check itself is the torch._assert_async call in dae/ctc.py.

@@ -165,6 +165,46 @@ def test_run_dynamic_eval_full_main_and_beamsearch(cuda, tmp_path):
     assert np.isfinite(wer2)
 
 
+def test_cli_beamsearch_flag_builds_the_lm_decoder(cuda, tmp_path, monkeypatch):
+    """`-beamsearch -kwargs lm_path=... lm_alpha=...` (run_dynamic_eval_full.py:56-65): the CLI builds the n-gram
+    BeamSearch itself, uses it for the in-loop pseudo-labels (lm_tta_beams) and the final decode (lm_eval_beams),
+    and the result equals passing the same decoder programmatically."""
+    from dae import ctc_beam_search, lib, run_dynamic_eval_full as r
+    from dae.ngram import write_synthetic_arpa
+    from dae.standin import SyntheticTokenizer, synthetic_recordings
+    V = TOY["C"] - 1
+    tok = SyntheticTokenizer(vocab_size=V, seed=0)
+    data = synthetic_recordings("tedlium", tokenizer=tok, scale=0.004)[:1]
+    arpa = str(tmp_path / "lm.arpa")
+    write_synthetic_arpa(arpa, V, order=3, counts=(None, 400, 600), seed=2)
+    argv = ['-beamsearch', '-seq', '1024', '-o', '512', '-d', 'tedlium', '-kwargs', f'lm_path={arpa}', 'lm_alpha=0.4016',
+            'lm_beta=1.625', 'lm_prune_less_than_val=3.221', 'lm_eval_beams=5', 'lm_tta_beams=3', 'optim_lr=1e-3',
+            'spec_augment_n_freq_masks=2', 'spec_augment_freq_mask_param=10']
+    widths = []
+    orig = ctc_beam_search.BeamSearch.__init__
+
+    def spy(self, *a, **k):
+        widths.append((k.get('beam_width'), k.get('alpha'), k.get('beta'), k.get('prune_less_than_val')))
+        return orig(self, *a, **k)
+    monkeypatch.setattr(ctc_beam_search.BeamSearch, "__init__", spy)
+    texts = {}
+    for how in ("cli", "programmatic"):
+        args = lib.apply_args(r.build_parser(), argv if how == "cli" else [a for a in argv if a != '-beamsearch'])
+        args.config = TOY_CONFIG
+        model = ToyModel(TOY["C"], seed=TOY["model_seed"])
+        captured = []
+        bs = None if how == "cli" else lib.load_beamsearch(arpa, alpha=0.4016, beta=1.625, prune_less_than_val=3.221,
+                                                           tokenizer=tok)
+        wer = r.main(args, model=model, tokenizer=tok, data=data, normalize=lambda s: captured.append(s) or s,
+                     beamsearch=bs)
+        assert np.isfinite(wer)
+        texts[how] = (captured, wer)
+    assert texts["cli"] == texts["programmatic"]
+    n_windows = sum(1 for w in widths if w[0] == 3)
+    assert n_windows >= 2 and sum(1 for w in widths if w[0] == 5) == 2          # in-loop beams 3, final decode beams 5
+    assert all(w[1:] == (0.4016, 1.625, 3.221) for w in widths)
+
+
 def test_adapt_on_concat_only_equals_return_params(cuda):
     """run_half_concat_eval.py:64-160: the adapt-only pass yields the same parameters as return_params=True."""
     from dae import lib

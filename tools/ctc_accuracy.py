@@ -1,6 +1,7 @@
 import os, sys, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 from oracle import ctc_oracle
+from dae import _C
 from dae.ctc import ctc_loss
 from dae.greedy import greedy_ids_device
 sys.path.insert(0, '/root/repo/tests')
@@ -14,7 +15,7 @@ il = torch.tensor([T], device='cuda'); tl = torch.tensor([lab.numel()], device='
 nll64, g64 = ctc_oracle.ctc_loss_grad(post.double().cpu().numpy(), tg.cpu().numpy(), [T], [lab.numel()], C - 1, gout=1.0 / T)
 lp64 = post.double().cpu().numpy()
 for path in ("0", "1"):
-    os.environ["DAE_CTC_BLOCKED"] = path
+    _C.ctc_configure(blocked=int(path))
     x = post.clone().requires_grad_()
     nll = ctc_loss(x, tg, il, tl, blank=C - 1, reduction="none")
     (nll.sum() / T).backward()

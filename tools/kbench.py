@@ -153,7 +153,7 @@ def main():
             go = torch.ones(B, device="cuda")
             med, best = tm.time(lambda: softdtw_backward(W, go), max(5, args.iters // 2))
             report("softdtw_bwd", [B, N, M], 3 * B * N * M * 4, med, best)
-            del D, R, Dc
+            del D, W
 
     if want("beam"):
         import numpy as np

@@ -23,12 +23,17 @@ _PROTOS = {
     "dae_abi_version": (c_int, []),
     "dae_error_string": (c_char_p, [c_int]),
     "dae_launch_count": (c_int64, []),
+    "dae_greedy_scratch_bytes": (c_size_t, []),
     "dae_greedy_collapse": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int,
-                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dae_collapse_path": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dae_specaug_scratch_bytes": (c_size_t, []),
     "dae_specaug_repeat": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                    c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dae_window_slices": (c_int, []),
+    "dae_window_sums": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "dae_specaug_repeat_premean": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                                           c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dae_cutout_scratch_bytes": (c_size_t, [c_int]),
     "dae_cutout": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "dae_frame_shuffle": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -57,7 +57,27 @@ class SpecAugment(torch.nn.Module):
         fb = draw_bands(B, self.n_freq_masks, self.freq_mask_param, F, generator)
         return fb, tb
 
-    def forward(self, specgram: torch.Tensor, lengths=None, n_clean: int = 0, bands=None):
+    @staticmethod
+    def window_sums(spec: torch.Tensor, starts, lens):
+        """Partial sums of every window ``spec[:, :, s:s+l]`` of a recording in ONE launch (dae_window_sums):
+        -> float64 [n_win, dae_window_slices()] on the device.  Row w goes to ``forward(..., window_sums=sums[w])``,
+        which then needs no reduction pass and no grid barrier of its own."""
+        _C.require_cuda(spec, "spec")
+        x = spec[0] if spec.dim() == 3 else spec
+        if x.dtype != torch.float32 or x.stride(1) != 1:
+            raise _C.DaeError("window_sums needs an fp32 spectrogram with contiguous time axis")
+        lib, dev = _C.lib(), x.device
+        n = len(starts)
+        ws = torch.tensor(list(starts), dtype=torch.int64).to(dev, non_blocking=True)
+        wl = torch.tensor(list(lens), dtype=torch.int64).to(dev, non_blocking=True)
+        sums = torch.empty((n, lib.dae_window_slices()), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev), prof.span("window_sums", int(sum(lens)) * x.shape[0] * 4):
+            rc = lib.dae_window_sums(x.data_ptr(), x.stride(0), x.shape[0], ws.data_ptr(), wl.data_ptr(), n,
+                                     sums.data_ptr(), _C.stream_ptr(dev))
+        _C.check(rc, "dae_window_sums")
+        return sums
+
+    def forward(self, specgram: torch.Tensor, lengths=None, n_clean: int = 0, bands=None, window_sums=None):
         """specgram [B,F,T] (or [F,T]) fp32 on the GPU -> masked copy, same shape.
 
         With ``n_clean=k`` the result is [B+k, F, T]: the B masked items followed by k verbatim
@@ -81,7 +101,17 @@ class SpecAugment(torch.nn.Module):
         nf, nt = int(fb.shape[1]), int(tb.shape[1])
         st = _C.stream_ptr(dev)
         with torch.cuda.device(dev), prof.span("specaug_repeat", (1 + B + n_clean) * F * T * 4):
-            if n_clean:
+            if n_clean and window_sums is not None:
+                # the window's partial sums are known (SpecAugment.window_sums): one plain single-pass launch
+                src = x[0]
+                if src.stride(1) != 1:
+                    src = src.contiguous()
+                fbc, tbc = fb.contiguous(), tb.contiguous()
+                rc = lib.dae_specaug_repeat_premean(src.data_ptr(), src.stride(0), F, T, fbc.data_ptr() if nf else None,
+                                                    nf, tbc.data_ptr() if nt else None, nt, int(self.zero_masking), B,
+                                                    n_clean, out.data_ptr(), window_sums.data_ptr(), None, st)
+                _C.check(rc, "dae_specaug_repeat_premean")
+            elif n_clean:
                 # one launch pair: B masked copies + n_clean clean copies of the shared window
                 src = x[0]
                 if src.stride(1) != 1:

@@ -111,6 +111,17 @@ __device__ __forceinline__ void stage_tile(T* sm, const T* __restrict__ mat, int
   constexpr int kRowsPerIt = 32 / kLanesPerRow;        // 4 or 2
   const int cbase = FLIP ? (M - c0 - kTile) : c0;
   T* dst0 = sm + ((c0 >> 5) & (kRing - 1)) * kTile;
+  if (vec && r0 + kBand <= N && cbase >= 0 && cbase + kTile <= M) {
+    // interior tile (all but the last band / last tile): no bounds checks, one pointer pair stepped by rows
+    const int rsub = lane / kLanesPerRow, x = (lane % kLanesPerRow) * kPer;
+    const int row = FLIP ? (N - 1 - (r0 + rsub)) : (r0 + rsub);
+    const T* src = mat + (int64_t)row * M + cbase + x;
+    T* dst = dst0 + rsub * kRingCols + x;
+    const int64_t sstep = (FLIP ? -(int64_t)kRowsPerIt : (int64_t)kRowsPerIt) * M;
+#pragma unroll
+    for (int it = 0; it < kBand / kRowsPerIt; ++it) cp_async16(dst + it * kRowsPerIt * kRingCols, src + it * sstep);
+    return;
+  }
   if (vec) {
 #pragma unroll
     for (int it = 0; it < kBand / kRowsPerIt; ++it) {
@@ -152,6 +163,18 @@ __device__ __forceinline__ void flush_tile(const T* sm, T* __restrict__ mat, int
   constexpr int kRowsPerIt = 32 / kLanesPerRow;
   const int cbase = FLIP ? (M - c0 - kTile) : c0;
   const T* src0 = sm + ((c0 >> 5) & 1) * kTile;
+  if (vec && r0 + kBand <= N && cbase >= 0 && cbase + kTile <= M) {
+    const int rsub = lane / kLanesPerRow, x = (lane % kLanesPerRow) * kPer;
+    const int row = FLIP ? (N - 1 - (r0 + rsub)) : (r0 + rsub);
+    T* dst = mat + (int64_t)row * M + cbase + x;
+    const T* src = src0 + rsub * kOutCols + x;
+    const int64_t dstep = (FLIP ? -(int64_t)kRowsPerIt : (int64_t)kRowsPerIt) * M;
+#pragma unroll
+    for (int it = 0; it < kBand / kRowsPerIt; ++it)
+      st_stream4(reinterpret_cast<float*>(dst + it * dstep),
+                 *reinterpret_cast<const float4*>(src + it * kRowsPerIt * kOutCols));
+    return;
+  }
   if (vec) {
 #pragma unroll
     for (int it = 0; it < kBand / kRowsPerIt; ++it) {

@@ -122,7 +122,131 @@ specaug_fused_kernel(const float* __restrict__ x, int64_t sF, int F, int T, doub
   }
 }
 
+// ---- window means computed once per recording + a barrier-free single-pass mask/copy kernel ------------------
+// The adapt loop augments every window of a recording (lcasr/lib.py:537-541); the fill value of a window is its
+// mean, a function of the spectrogram alone.  dae_window_sums leaves kWinSlices fp64 partial sums per window in ONE
+// launch per recording; dae_specaug_repeat_premean then needs neither a grid barrier nor a second pass: every CTA
+// adds the window's partials in the same fixed order and streams x -> [masked..., clean...] once.
+constexpr int kWinSlices = 16;
+
+__global__ void __launch_bounds__(256)
+window_sums_kernel(const float* __restrict__ x, int64_t sF, int F, const int64_t* __restrict__ win_start,
+                   const int64_t* __restrict__ win_len, double* __restrict__ sums) {
+  __shared__ double red[8];
+  const int w = blockIdx.y, slice = blockIdx.x;
+  const int64_t t0 = win_start[w], T = win_len[w];
+  const int64_t n = (int64_t)F * T;
+  const int64_t per = (n + kWinSlices - 1) / kWinSlices;
+  const int64_t lo = slice * per, hi = lo + per < n ? lo + per : n;
+  double acc = 0.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const int64_t f = i / T, c = i - f * T;
+    acc += (double)__ldg(x + f * sF + t0 + c);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k];
+    sums[(int64_t)w * kWinSlices + slice] = s;
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+specaug_premean_kernel(const float* __restrict__ x, int64_t sF, int F, int T, const double* __restrict__ win_sums,
+                       int zero_masking, int n_clean, const __grid_constant__ BandSet bands,
+                       float* __restrict__ out, float* __restrict__ mean_out) {
+  float fill = 0.0f;
+  if (!zero_masking) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kWinSlices; ++k) s += __ldg(win_sums + k);
+    fill = (float)(s / ((double)F * (double)T));
+  }
+  if (mean_out && blockIdx.x == 0 && threadIdx.x == 0) *mean_out = fill;
+  const int64_t plane = (int64_t)F * T;
+  const int t4 = T >> 2;
+  const int64_t n_items = VEC ? (int64_t)F * t4 : plane;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_items; i += (int64_t)gridDim.x * 256) {
+    if (VEC) {
+      const int f = (int)(i / t4), c = 4 * (int)(i - (int64_t)f * t4);
+      const float4 v = ld_stream4(x + f * sF + c);
+      const int64_t o = (int64_t)f * T + c;
+      for (int a = 0; a < bands.n_aug; ++a) {
+        float4 m = v;
+        if (in_bands(bands.f[a], bands.nf, f)) {
+          m = make_float4(fill, fill, fill, fill);
+        } else if (bands.nt) {
+          if (in_bands(bands.t[a], bands.nt, c)) m.x = fill;
+          if (in_bands(bands.t[a], bands.nt, c + 1)) m.y = fill;
+          if (in_bands(bands.t[a], bands.nt, c + 2)) m.z = fill;
+          if (in_bands(bands.t[a], bands.nt, c + 3)) m.w = fill;
+        }
+        st_stream4(out + a * plane + o, m);
+      }
+      for (int k = 0; k < n_clean; ++k) st_stream4(out + (bands.n_aug + k) * plane + o, v);
+    } else {
+      const int f = (int)(i / T), c = (int)(i - (int64_t)f * T);
+      const float v = x[f * sF + c];
+      for (int a = 0; a < bands.n_aug; ++a)
+        out[a * plane + i] = (in_bands(bands.f[a], bands.nf, f) || in_bands(bands.t[a], bands.nt, c)) ? fill : v;
+      for (int k = 0; k < n_clean; ++k) out[(bands.n_aug + k) * plane + i] = v;
+    }
+  }
+}
+
+static int fill_bands(BandSet& bs, const int32_t* fmask_host, int nf, const int32_t* tmask_host, int nt, int n_aug) {
+  if (nf < 0 || nt < 0 || n_aug < 0) return DAE_E_BADARG;
+  if (nf > kMaxBands || nt > kMaxBands || n_aug > kMaxAug) return DAE_E_TOOBIG;
+  if ((nf && !fmask_host) || (nt && !tmask_host)) return DAE_E_BADARG;
+  bs.n_aug = n_aug; bs.nf = nf; bs.nt = nt;
+  for (int a = 0; a < n_aug; ++a) {
+    for (int k = 0; k < nf; ++k) bs.f[a][k] = make_int2(fmask_host[(a * nf + k) * 2], fmask_host[(a * nf + k) * 2 + 1]);
+    for (int k = 0; k < nt; ++k) bs.t[a][k] = make_int2(tmask_host[(a * nt + k) * 2], tmask_host[(a * nt + k) * 2 + 1]);
+  }
+  return 0;
+}
+
 }  // namespace dae
+
+extern "C" int dae_window_slices(void) { return dae::kWinSlices; }
+
+extern "C" int dae_window_sums(const float* x, int64_t sF, int F, const int64_t* win_start, const int64_t* win_len,
+                               int n_win, double* sums, void* stream) {
+  using namespace dae;
+  if (!x || !win_start || !win_len || !sums || F <= 0 || n_win < 0) return DAE_E_BADARG;
+  if (n_win == 0) return 0;
+  if (n_win > 65535) return DAE_E_TOOBIG;
+  window_sums_kernel<<<dim3(kWinSlices, n_win), 256, 0, (cudaStream_t)stream>>>(x, sF, F, win_start, win_len, sums);
+  DAE_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int dae_specaug_repeat_premean(const float* x, int64_t sF, int F, int T, const int32_t* fmask_host, int nf,
+                                          const int32_t* tmask_host, int nt, int zero_masking, int n_aug, int n_clean,
+                                          float* out, const double* win_sums, float* mean_out, void* stream) {
+  using namespace dae;
+  if (!x || !out || F <= 0 || T <= 0 || n_clean < 0) return DAE_E_BADARG;
+  BandSet bs;
+  const int rc = fill_bands(bs, fmask_host, nf, tmask_host, nt, n_aug);
+  if (rc) return rc;
+  if (!zero_masking && n_aug > 0 && !win_sums) return DAE_E_BADARG;
+  if (n_aug + n_clean == 0) return 0;
+  const bool vec = aligned16(x) && aligned16(out) && (T % 4 == 0) && (sF % 4 == 0);
+  const int64_t n_items = vec ? (int64_t)F * (T >> 2) : (int64_t)F * T;
+  int64_t want = (n_items + 255) / 256;
+  const int grid = (int)(want < (int64_t)kNumSMs * 8 ? want : (int64_t)kNumSMs * 8);
+  const int zm = (zero_masking || n_aug == 0) ? 1 : 0;
+  if (vec)
+    specaug_premean_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, sF, F, T, win_sums, zm, n_clean, bs, out, mean_out);
+  else
+    specaug_premean_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, sF, F, T, win_sums, zm, n_clean, bs, out, mean_out);
+  DAE_LAUNCH_OK();
+  return 0;
+}
 
 extern "C" size_t dae_specaug_scratch_bytes(void) { return sizeof(double) * dae::kSumGrid + 64; }
 

@@ -12,6 +12,17 @@ import torch
 from . import _C, prof
 
 
+_sync_words = {}
+
+
+def _sync_word(dev):
+    """One zero-initialised scratch word per (device, stream): the fused kernel's last-CTA ticket (self-resetting)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    if key not in _sync_words:
+        _sync_words[key] = torch.zeros(_C.lib().dae_greedy_scratch_bytes(), dtype=torch.uint8, device=dev)
+    return _sync_words[key]
+
+
 def greedy_ids_device(emission: torch.Tensor, blank_id: int, lengths: torch.Tensor = None):
     """emission [T,C] or [B,T,C] fp32 CUDA -> (path [B,T] i32, ids [B,T] i32, n_ids [B] i32), all on device."""
     _C.require_cuda(emission, "emission")
@@ -32,7 +43,7 @@ def greedy_ids_device(emission: torch.Tensor, blank_id: int, lengths: torch.Tens
     with torch.cuda.device(dev), prof.span("greedy_collapse", B * T * C * 4):
         rc = _C.lib().dae_greedy_collapse(x.data_ptr(), x.stride(0), x.stride(1), B, T, C, _C.ptr(lengths),
                                           int(blank_id), path.data_ptr(), ids.data_ptr(), n_ids.data_ptr(),
-                                          _C.stream_ptr(dev))
+                                          _sync_word(dev).data_ptr(), _C.stream_ptr(dev))
     _C.check(rc, "dae_greedy_collapse")
     return path, ids, n_ids
 

@@ -239,6 +239,12 @@ def dynamic_eval_ctc_loss(
     training_data, training_keys = prepare_chunks(spec_dev, seq_len, overlap)
     tm.add('h2d', time.perf_counter() - t0)
 
+    # every window's mean (SpecAugment's fill value) in one launch per recording
+    win_sums = None
+    if not spec_augment_config['zero_masking'] and (spec_augment_config['n_freq_masks'] or spec_augment_config['n_time_masks']) \
+            and d.get('epochs', 1) > 0 and spec_dev.dim() == 3 and spec_dev.stride(2) == 1:
+        sums = SpecAugment.window_sums(spec_dev, training_keys, [int(training_data[i].shape[-1]) for i in training_keys])
+        win_sums = {i: sums[k] for k, i in enumerate(training_keys)}
     C = model.decoder.num_classes
     kept = {}                                               # online: teacher posteriors of each window
     step_log = []
@@ -249,7 +255,8 @@ def dynamic_eval_ctc_loss(
         for i in keys:
             window = training_data[i]                       # [1,F,T] view
             u_len = window.shape[-1]
-            audio_chunk = augmentation(window.expand(num_negatives, -1, -1), n_clean=1)   # [aug..., clean]
+            audio_chunk = augmentation(window.expand(num_negatives, -1, -1), n_clean=1,   # [aug..., clean]
+                                       window_sums=None if win_sums is None else win_sums[i])
             if frame_shuffle_args['time_dimension'] or frame_shuffle_args['freq_dimension']:
                 audio_chunk[:num_negatives] = frame_shuffle(audio_chunk[:num_negatives], **frame_shuffle_args)
             if random_noise:

@@ -52,10 +52,14 @@ int64_t     dae_launch_count(void);
  *                 as torch.argmax)
  * ids     [B,T] int32 out: collapsed label ids, ids[b, 0 .. n_ids[b])
  * n_ids   [B]   int32 out
+ * scratch dae_greedy_scratch_bytes() bytes that are ZERO on entry (the call leaves them zero again, so one
+ *         zero-initialised buffer per stream serves every call): argmax and collapse then run as ONE launch, the
+ *         last CTA to finish doing the collapse.  NULL = two launches, no scratch needed.
  * ------------------------------------------------------------------------------------ */
+size_t dae_greedy_scratch_bytes(void);
 int dae_greedy_collapse(const float* lp, int64_t sB, int64_t sT, int B, int T, int C,
                         const int32_t* lengths, int blank,
-                        int32_t* path, int32_t* ids, int32_t* n_ids, void* stream);
+                        int32_t* path, int32_t* ids, int32_t* n_ids, void* scratch, void* stream);
 
 /* Collapse an already computed per-frame argmax path (e.g. dae_stitch's fused `path` output):
  * same collapse as above without the argmax pass.  path [B,T] int32, ids [B,T], n_ids [B]. */
@@ -82,6 +86,21 @@ int dae_specaug_repeat(const float* x, int64_t sF, int F, int T,
                        const int32_t* fmask_host, int nf, const int32_t* tmask_host, int nt,
                        int zero_masking, int n_aug, int n_clean,
                        float* out, void* partials, float* mean_out, void* stream);
+
+/* Per-recording variant used by the adapt loop (every window of a recording is augmented, lcasr/lib.py:537-541,
+ * and a window's fill value is its mean — a function of the spectrogram alone):
+ * dae_window_sums: ONE launch per recording leaves dae_window_slices() fp64 partial sums per window,
+ *            sums[w][k] = sum of the k-th slice of x[:, win_start[w] : win_start[w]+win_len[w]] (fixed order).
+ *            x [F, spec_n] fp32 row stride sF; win_start / win_len [n_win] int64 DEVICE arrays.
+ * dae_specaug_repeat_premean: dae_specaug_repeat for a window whose partial sums are already known (win_sums =
+ *            &sums[w][0], device): one ordinary launch, x read once, no grid barrier, no scratch. */
+int dae_window_slices(void);
+int dae_window_sums(const float* x, int64_t sF, int F, const int64_t* win_start, const int64_t* win_len, int n_win,
+                    double* sums, void* stream);
+int dae_specaug_repeat_premean(const float* x, int64_t sF, int F, int T,
+                               const int32_t* fmask_host, int nf, const int32_t* tmask_host, int nt,
+                               int zero_masking, int n_aug, int n_clean,
+                               float* out, const double* win_sums, float* mean_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * (f-3) cutout: rectangles of the augmented window overwritten in place.

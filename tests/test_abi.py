@@ -36,7 +36,7 @@ def test_scratch_sizes_and_errors():
     assert big >= 2 * 2048 * 1201 * 4
     assert b"bad argument" in lib.dae_error_string(-1)
     # argument validation happens before any CUDA call, so it is testable without a GPU
-    assert lib.dae_greedy_collapse(None, 0, 0, 1, 1, 1, None, 0, None, None, None, None) == -1
+    assert lib.dae_greedy_collapse(None, 0, 0, 1, 1, 1, None, 0, None, None, None, None, None) == -1
     assert lib.dae_ctc_lattice(None, 0, 0, 1, 1, 1, None, 0, 0, None, None, 0, None, None, 0, None) == -1
 
 

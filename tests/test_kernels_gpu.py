@@ -95,6 +95,32 @@ def test_specaug_repeat_matches_oracle(cuda, F, T, nf, nt, zero):
     np.testing.assert_array_equal(got, ref2)                                   # given the fill: bit-exact
 
 
+def test_specaug_with_precomputed_window_sums(cuda):
+    """The adapt loop's variant: dae_window_sums once per recording, then one barrier-free launch per window.  Same
+    result as the self-contained call: clean copy and everything outside the bands bit-exact, fill = the window's mean."""
+    from dae.augment import SpecAugment
+    torch.manual_seed(21)
+    spec = (torch.randn(1, 80, 40000) * 1.7 - 0.2)
+    dspec = spec.to(cuda)
+    starts, lens = [0, 2048, 20000, 30000], [16384, 16384, 16384, 10000]      # the last window is the ragged one
+    sums = SpecAugment.window_sums(dspec, starts, lens)
+    assert sums.shape[0] == 4 and sums.dtype == torch.float64
+    for w, (s0, ln) in enumerate(zip(starts, lens)):
+        win = spec[0, :, s0:s0 + ln].numpy()
+        assert abs(float(sums[w].sum()) - float(win.astype(np.float64).sum())) <= 1e-9 * ln * 80
+        aug = SpecAugment(n_time_masks=2 if w == 3 else 0, n_freq_masks=6, freq_mask_param=34, time_mask_param=40)
+        out = aug(dspec[:, :, s0:s0 + ln], n_clean=1, window_sums=sums[w])
+        fb, tb = aug.last_bands
+        _, fill = specaug_oracle.specaug_repeat(win, fb.tolist(), tb.tolist(), False, 1)
+        got = out.cpu().numpy()
+        kfill = got[0][got[0] != win][0]
+        assert abs(float(kfill) - float(fill)) <= 1.2e-7 * max(1.0, abs(float(fill)))
+        ref, _ = specaug_oracle.specaug_repeat(win, fb.tolist(), tb.tolist(), False, 1, fill=kfill)
+        np.testing.assert_array_equal(got, ref)
+        same = aug(dspec[:, :, s0:s0 + ln], n_clean=1, bands=(fb, tb))          # self-contained path, same bands
+        assert torch.equal(same[1], out[1]) and float((same[0] - out[0]).abs().max()) <= 1.2e-7 * max(1.0, abs(float(fill)))
+
+
 def test_specaug_plain_call_and_determinism(cuda):
     from dae.augment import SpecAugment
     torch.manual_seed(3)

@@ -87,8 +87,8 @@ def test_cuda_full_matrix_R(cuda):
             w_up = np.exp((Rp[:, 1:-1, 1:-1] - D.numpy() - Rp[:, :-2, 1:-1]) / gamma)      # weight of (i-1, j)
             w_left = np.exp((Rp[:, 1:-1, 1:-1] - D.numpy() - Rp[:, 1:-1, :-2]) / gamma)   # weight of (i, j-1)
         Wc = W.cpu().numpy()
-        np.testing.assert_allclose(Wc[..., 0][fin], np.nan_to_num(w_up)[fin], rtol=0, atol=2e-6)
-        np.testing.assert_allclose(Wc[..., 1][fin], np.nan_to_num(w_left)[fin], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(Wc[..., 0][fin], np.nan_to_num(w_up)[fin], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(Wc[..., 1][fin], np.nan_to_num(w_left)[fin], rtol=0, atol=1e-5)
         assert (Wc[~fin] == 0).all()
 
 

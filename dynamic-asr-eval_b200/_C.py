@@ -62,6 +62,7 @@ _PROTOS = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 ctypes.c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dae_ctc_rescale": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int64, ctypes.c_float, c_void_p]),
     "dae_stitch": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64,
                            c_void_p, c_void_p, c_void_p]),
 }

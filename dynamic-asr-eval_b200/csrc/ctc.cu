@@ -486,3 +486,31 @@ extern "C" int dae_ctc_grad(const float* lp, int64_t sT, int64_t sN, int T, int 
   DAE_LAUNCH_OK();
   return 0;
 }
+
+namespace dae {
+// grad[t,n,:] *= gout[n] / hint wherever that ratio is not exactly 1 (the gradient was formed in the forward call
+// with the caller's expected upstream scale; in the adapt loop the ratio is 1 and every CTA returns after one load).
+__global__ void __launch_bounds__(256)
+ctc_rescale_kernel(float* __restrict__ grad, int T, int N, int C, const float* __restrict__ gout, int64_t gout_stride,
+                   float hint) {
+  const int n = blockIdx.y;
+  const float g = gout[(int64_t)n * gout_stride];
+  if (g == hint) return;
+  const float r = g / hint;
+  for (int t = blockIdx.x; t < T; t += gridDim.x) {
+    float* row = grad + ((int64_t)t * N + n) * C;
+    for (int c = threadIdx.x; c < C; c += 256) row[c] *= r;
+  }
+}
+}  // namespace dae
+
+extern "C" int dae_ctc_rescale(float* grad, int T, int N, int C, const float* gout, int64_t gout_stride, float hint,
+                               void* stream) {
+  using namespace dae;
+  if (!grad || !gout || T < 0 || N < 0 || C <= 0 || !(hint != 0.0f)) return DAE_E_BADARG;
+  if (T == 0 || N == 0) return 0;
+  const int gx = T < kNumSMs * 4 ? T : kNumSMs * 4;
+  ctc_rescale_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>(grad, T, N, C, gout, gout_stride, hint);
+  DAE_LAUNCH_OK();
+  return 0;
+}

@@ -13,7 +13,7 @@ from . import _C, prof
 
 class _CTCFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, log_probs, targets, input_lengths, target_lengths, blank, validate=True):
+    def forward(ctx, log_probs, targets, input_lengths, target_lengths, blank, validate=True, grad_scale_hint=None):
         _C.require_cuda(log_probs, "log_probs")
         if log_probs.dtype != torch.float32:
             raise _C.DaeError("dae.CTCLoss computes in fp32; got " + str(log_probs.dtype))
@@ -60,12 +60,41 @@ class _CTCFunction(torch.autograd.Function):
                                      in_len.data_ptr(), tg_len.data_ptr(), int(blank),
                                      nll.data_ptr(), scratch.data_ptr(), nbytes, _C.stream_ptr(dev))
         _C.check(rc, "dae_ctc_lattice")
-        ctx.save_for_backward(lp, tg, in_len, tg_len, nll, scratch)
         ctx.blank = int(blank)
+        ctx.hint = None
+        if grad_scale_hint is not None and log_probs.requires_grad:
+            # the reference's `loss / (T*N); loss.backward()` (lcasr/lib.py:573-579): the upstream scale is known
+            # now, so the gradient launch follows the lattice launches directly; backward() only checks the scale
+            ctx.hint = float(grad_scale_hint)
+            g = torch.full((1,), ctx.hint, dtype=torch.float32, device=dev)
+            grad = torch.empty((T, N, C), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev), prof.span("ctc_grad", 2 * T * N * C * 4):
+                rc = lib.dae_ctc_grad(lp.data_ptr(), lp.stride(0), lp.stride(1), T, N, C,
+                                      tg.data_ptr() if Lmax else None, tg.stride(0), Lmax,
+                                      in_len.data_ptr(), tg_len.data_ptr(), int(blank), nll.data_ptr(), g.data_ptr(), 0,
+                                      grad.data_ptr(), scratch.data_ptr(), nbytes, _C.stream_ptr(dev))
+            _C.check(rc, "dae_ctc_grad")
+            ctx.save_for_backward(grad)
+            ctx.shape = (T, N, C)
+            return nll
+        ctx.save_for_backward(lp, tg, in_len, tg_len, nll, scratch)
         return nll
 
     @staticmethod
     def backward(ctx, grad_nll):
+        if ctx.hint is not None:
+            grad, = ctx.saved_tensors
+            T, N, C = ctx.shape
+            g = grad_nll.to(torch.float32)
+            if g.numel() == 1:
+                g, g_stride = g.reshape(1), 0
+            else:
+                g, g_stride = g.contiguous(), 1
+            with torch.cuda.device(grad.device):
+                rc = _C.lib().dae_ctc_rescale(grad.data_ptr(), T, N, C, g.data_ptr(), g_stride, ctx.hint,
+                                              _C.stream_ptr(grad.device))
+            _C.check(rc, "dae_ctc_rescale")
+            return (grad[:, 0] if ctx.unbatched else grad), None, None, None, None, None, None
         lp, tg, in_len, tg_len, nll, scratch = ctx.saved_tensors
         T, N, C = lp.shape
         unbatched = ctx.unbatched
@@ -85,17 +114,19 @@ class _CTCFunction(torch.autograd.Function):
                                        nll.data_ptr(), g.data_ptr(), g_stride, grad.data_ptr(),
                                        scratch.data_ptr(), scratch.numel(), _C.stream_ptr(lp.device))
         _C.check(rc, "dae_ctc_grad")
-        return (grad[:, 0] if unbatched else grad), None, None, None, None, None
+        return (grad[:, 0] if unbatched else grad), None, None, None, None, None, None
 
 
 def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reduction="mean", zero_infinity=False,
-             validate=True):
+             validate=True, grad_scale_hint=None):
     """Functional form, same argument meaning as ``torch.nn.functional.ctc_loss``.  ``validate=False`` skips the
     device-side label range check (the adapt loop's labels come straight from the tokenizer)."""
     if zero_infinity:
         raise _C.DaeError("zero_infinity=True is not used by the reference (SURVEY.md appendix A) and is not implemented")
     unbatched = log_probs.dim() == 2
-    nll = _CTCFunction.apply(log_probs, targets, input_lengths, target_lengths, blank, validate)
+    if grad_scale_hint is not None and reduction != "sum":
+        raise _C.DaeError("grad_scale_hint assumes reduction='sum' (every sample sees the same upstream gradient)")
+    nll = _CTCFunction.apply(log_probs, targets, input_lengths, target_lengths, blank, validate, grad_scale_hint)
     if reduction == "sum":
         return nll.sum()
     if reduction == "none":
@@ -112,6 +143,13 @@ class CTCLoss(torch.nn.Module):
     def __init__(self, blank: int = 0, reduction: str = "mean", zero_infinity: bool = False, validate: bool = True):
         super().__init__()
         self.blank, self.reduction, self.zero_infinity, self.validate = blank, reduction, zero_infinity, validate
+
+    def with_scale(self, log_probs, targets, input_lengths, target_lengths, grad_scale_hint):
+        """Same loss; the gradient is formed right away for the upstream scale the caller is about to apply
+        (``loss * grad_scale_hint`` then ``.backward()``), see _CTCFunction.forward.  Any other upstream gradient
+        still gives the right result (dae_ctc_rescale)."""
+        return ctc_loss(log_probs, targets, input_lengths, target_lengths, self.blank, self.reduction,
+                        self.zero_infinity, self.validate, grad_scale_hint)
 
     def forward(self, log_probs, targets, input_lengths, target_lengths):
         return ctc_loss(log_probs, targets, input_lengths, target_lengths, self.blank, self.reduction,

@@ -275,9 +275,10 @@ def dynamic_eval_ctc_loss(
             augmented_outs = post[:num_negatives]
             N, B = augmented_outs.shape[1], augmented_outs.shape[0]
             total_tokens_in_loss = N * B
-            loss = ctc_loss_fn(augmented_outs.transpose(0, 1), pseudo,
-                               torch.full((B,), N, dtype=torch.long, device=device),
-                               torch.full((B,), pseudo.shape[1], dtype=torch.long, device=device)) / total_tokens_in_loss
+            loss = ctc_loss_fn.with_scale(augmented_outs.transpose(0, 1), pseudo,
+                                          torch.full((B,), N, dtype=torch.long, device=device),
+                                          torch.full((B,), pseudo.shape[1], dtype=torch.long, device=device),
+                                          grad_scale_hint=1.0 / total_tokens_in_loss) / total_tokens_in_loss
             optimizer.zero_grad(set_to_none=True)
             loss.backward()
             optimizer.step()

@@ -162,6 +162,14 @@ int dae_ctc_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C,
                  const float* nll, const float* gout, int64_t gout_stride,
                  float* grad, const void* scratch, size_t scratch_bytes, void* stream);
 
+/* The reference always follows the loss with `/ (T*N)` and `.backward()` (lcasr/lib.py:573-579), so the upstream
+ * gradient is known when the loss is computed: a caller may run dae_ctc_grad right after dae_ctc_lattice with the
+ * expected scale `hint` (both launches back to back, no host round trip in between) and, when the real upstream
+ * gradient arrives, call dae_ctc_rescale: grad[t,n,:] *= gout[n]/hint where that ratio is not exactly 1 — a
+ * kernel whose CTAs return after one load in the expected case. */
+int dae_ctc_rescale(float* grad, int T, int N, int C, const float* gout, int64_t gout_stride, float hint,
+                    void* stream);
+
 /* Debug/test switch for which CTC lattice implementation dae_ctc_lattice and dae_ctc_scratch_bytes pick
  * (process-wide; seeded once from the environment variables DAE_CTC_BLOCKED / DAE_CTC_CLUSTER / DAE_CTC_PAIRS):
  *   blocked  -1 = by shape (default), 0 = always the per-frame chain, 1 = the time-blocked scan whenever it fits

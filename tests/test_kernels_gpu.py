@@ -448,3 +448,26 @@ def test_ctc_rejects_out_of_range_labels(cuda):
     torch.cuda.synchronize()
     # The failing case is NOT run here: a device-side assert kills the CUDA context and is logged by the driver
     # as a GPU fault on this shared pool; the check itself is the torch._assert_async call in dae/ctc.py.
+
+
+def test_ctc_gradient_formed_in_forward_with_scale_hint(cuda, ctc_path):
+    """CTCLoss.with_scale (the adapt loop's `loss / (T*N); backward()`): same loss, gradient bit-identical to the
+    two-call path when the upstream gradient equals the hint, rescaled correctly when it does not."""
+    from dae.ctc import CTCLoss
+    T, N, C, L = 200, 2, 50, 23
+    g = torch.Generator().manual_seed(12)
+    lp = (torch.randn(T, N, C, generator=g) * 2).log_softmax(-1).to(cuda)
+    tg = torch.randint(0, C - 1, (N, L), generator=g).to(cuda)
+    il, tl = torch.tensor([T, T - 17], device=cuda), torch.tensor([L, L - 5], device=cuda)
+    f = CTCLoss(blank=C - 1, reduction="sum")
+    a = lp.clone().requires_grad_()
+    (f(a, tg, il, tl) / (T * N)).backward()
+    b = lp.clone().requires_grad_()
+    lb = f.with_scale(b, tg, il, tl, grad_scale_hint=1.0 / (T * N))
+    (lb / (T * N)).backward()
+    assert torch.equal(a.grad, b.grad)
+    c = lp.clone().requires_grad_()
+    (f.with_scale(c, tg, il, tl, grad_scale_hint=1.0 / (T * N)) * 0.37).backward()       # a different upstream scale
+    torch.testing.assert_close(c.grad, a.grad * (0.37 * T * N), rtol=2e-6, atol=1e-12)
+    with torch.no_grad():                                                             # no grad required: lattice only
+        assert torch.equal(f.with_scale(lp, tg, il, tl, grad_scale_hint=0.5), lb.detach())

@@ -214,12 +214,33 @@ def aux_kernels(peak):
     write_synthetic_arpa(arpa, V, order=4, counts=(None, 900, 200000, 800000), seed=4, fast=True)
     order, grams = read_arpa(arpa)
     lm = NGramLM(grams, order, V)
+    offs = [int(v) for v in np.linspace(0, T, nseg + 1)]
+
+    def beam_case(name, lpb, lm_, dense, segs, note):
+        sr = _Search(lpb, segs, lm_, 100, 0.45, 1.53, V, 0.0, 0.0, -6, 3.17, n_best=1, dense_lm=dense)
+        med, _ = tm.time(lambda: sr.run_all(), 3, warmup=1)
+        st = sr.stats()
+        n_ctx = int((lm_.depth < lm_.order).sum())
+        rec(name, [T, V + 1, len(segs) - 1], T * (V + 1) * 4, med,
+            {"frames_per_s": T / med, "audio_hours_per_s": T / 50 / 3600 / med, "lm_nodes": lm_.n_nodes,
+             "lm_hbm_bytes": lm_.nbytes() + (8 * n_ctx * V if sr.row is not None else 0),
+             "lm_path": "dense row/next tables" if sr.row is not None else "trie walk (fail links + binary search)",
+             "candidates_per_frame": st["candidates"] / T, "ns_per_candidate": med * 1e9 / max(st["candidates"], 1),
+             "us_per_frame_per_segment": med * 1e6 / (T / (len(segs) - 1)),
+             "lm_loads": st["lm_loads"], "lm_probe_bytes_32B_sectors": 32 * st["lm_loads"],
+             "algorithmic_gbs_incl_lm_probes": (T * (V + 1) * 4 + 32 * st["lm_loads"]) / med / 1e9, "note": note})
+        del sr
     lpb = torch.from_numpy(peaky_log_probs(T, V + 1, V, 3, sharp=5.0)).cuda()
-    sr = _Search(lpb, [int(v) for v in np.linspace(0, T, nseg + 1)], lm, 100, 0.45, 1.53, V, 0.0, 0.0, -6, 3.17, n_best=1)
-    med, _ = tm.time(lambda: sr.run_all(), 3, warmup=1)
-    rec("beam_search[1h@50fps,V=32,beam=100,360 segments]", [T, V + 1, nseg], T * (V + 1) * 4, med,
-        {"frames_per_s": T / med, "audio_hours_per_s": T / 50 / 3600 / med, "lm_nodes": lm.n_nodes,
-         "lm_hbm_bytes": lm.nbytes() + 8 * int((lm.depth < lm.order).sum()) * V})
+    beam_case("beam_search[1h@50fps,V=32,beam=100,360 segments]", lpb, lm, True, offs,
+              "flat synthetic posteriors (sharp=5): ~25 of 32 classes pass the -6 AM threshold every frame")
+    beam_case("beam_search[1h,one sequence]", lpb, lm, True, [0, T], "the same hour as ONE sequence: per-frame latency")
+    big = NGramLM.synthetic(V, 5, 8_000_000, seed=4)
+    beam_case("beam_search[360 segments, 198 MB 5-gram trie walked in HBM]", lpb, big, False, offs,
+              "LM larger than L2 (8.2 M nodes), no dense tables: every LM query walks fail links in HBM")
+    del big
+    lps = torch.from_numpy(peaky_log_probs(T, V + 1, V, 3, sharp=12.0)).cuda()
+    beam_case("beam_search[360 segments, speech-like sharp posteriors]", lps, lm, True, offs,
+              "top class ~0.99 per frame (sharp=12), as trained CTC models emit: 1-3 candidate classes per frame")
     return out
 
 

@@ -64,43 +64,52 @@ __device__ __forceinline__ unsigned long long hash_push(unsigned long long h, in
   return x;
 }
 
-__device__ __forceinline__ int lm_find(const DaeNgram& lm, int node, int w) {
+// per-thread probe counter (global loads issued against the LM arrays), summed per segment into out_n[.,3]
+struct LmCount { int probes; };
+__device__ __forceinline__ int lm_find(const DaeNgram& lm, int node, int w, LmCount* cnt = nullptr) {
   int lo = __ldg(lm.cb + node), hi = __ldg(lm.cb + node + 1);
+  if (cnt) cnt->probes += 2;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     const int t = __ldg(lm.tok + mid);
+    if (cnt) cnt->probes += 1;
     if (t == w) return mid;
     if (t < w) lo = mid + 1; else hi = mid;
   }
   return -1;
 }
 // log p(w | state): longest context first, fp32 adds in that order (dae/ngram.py docstring).
-__device__ __forceinline__ float lm_score_walk(const DaeNgram& lm, int state, int w) {
+__device__ __forceinline__ float lm_score_walk(const DaeNgram& lm, int state, int w, LmCount* cnt = nullptr) {
   float acc = 0.0f;
   int cur = state;
   for (;;) {
-    const int c = lm_find(lm, cur, w);
+    const int c = lm_find(lm, cur, w, cnt);
+    if (cnt) cnt->probes += 1;
     if (c >= 0) return __fadd_rn(acc, __ldg(lm.logp + c));
     acc = __fadd_rn(acc, __ldg(lm.bo + cur));
     if (cur == 0) return __fadd_rn(acc, lm.unk_lp);
+    if (cnt) cnt->probes += 1;
     cur = __ldg(lm.fail + cur);
   }
 }
-__device__ __forceinline__ int lm_next_state_walk(const DaeNgram& lm, int state, int w) {
+__device__ __forceinline__ int lm_next_state_walk(const DaeNgram& lm, int state, int w, LmCount* cnt = nullptr) {
   int cur = state;
   for (;;) {
-    const int c = lm_find(lm, cur, w);
+    const int c = lm_find(lm, cur, w, cnt);
+    if (cnt) cnt->probes += 1;
     if (c >= 0 && __ldg(lm.depth + c) < lm.order) return c;
     if (cur == 0) return 0;
     cur = __ldg(lm.fail + cur);
   }
 }
 
-__device__ __forceinline__ float lm_score(const DaeNgram& lm, int state, int w) {
-  return lm.row ? __ldg(lm.row + (size_t)state * lm.V + w) : lm_score_walk(lm, state, w);
+__device__ __forceinline__ float lm_score(const DaeNgram& lm, int state, int w, LmCount* cnt) {
+  if (lm.row) { cnt->probes += 1; return __ldg(lm.row + (size_t)state * lm.V + w); }
+  return lm_score_walk(lm, state, w, cnt);
 }
-__device__ __forceinline__ int lm_next_state(const DaeNgram& lm, int state, int w) {
-  return lm.next ? __ldg(lm.next + (size_t)state * lm.V + w) : lm_next_state_walk(lm, state, w);
+__device__ __forceinline__ int lm_next_state(const DaeNgram& lm, int state, int w, LmCount* cnt) {
+  if (lm.next) { cnt->probes += 1; return __ldg(lm.next + (size_t)state * lm.V + w); }
+  return lm_next_state_walk(lm, state, w, cnt);
 }
 
 // Dense expansion of the trie: one thread per (context node, token), same device functions as the search,
@@ -188,6 +197,10 @@ beam_search_kernel(BeamParams P) {
   const int seg_lo = P.seg_off[g], seg_T = P.seg_off[g + 1] - seg_lo;
 
   __shared__ int nb_s, pos_s;
+  __shared__ unsigned long long stat_cand, stat_probe;
+  LmCount lmc{0};
+  unsigned my_cand = 0;
+  if (tid == 0) { stat_cand = 0ull; stat_probe = 0ull; }
   if (tid == 0) {
     if (P.t_begin == 0) {                      // initiate (:126-138): one beam, LM sequence [bos]
       BeamRec r;
@@ -312,11 +325,12 @@ beam_search_kernel(BeamParams P) {
       const int i = S.top_idx[k];
       const float am = S.top_am[k];
       const BeamRec& br = S.beams[b];
+      ++my_cand;
       float sc;
       if (cand_is_stay(br, i, blank)) {
         sc = __fadd_rn(__fadd_rn(am, br.score), i == blank ? P.blank_pen : P.rep_pen);
       } else {
-        const float lmv = __fadd_rn(__fmul_rn(lm_score(P.lm, br.lmst, i), P.alpha), P.beta);
+        const float lmv = __fadd_rn(__fmul_rn(lm_score(P.lm, br.lmst, i, &lmc), P.alpha), P.beta);
         sc = __fadd_rn(__fadd_rn(am, lmv), br.score);
       }
       S.c_score[c] = sc;
@@ -406,7 +420,7 @@ beam_search_kernel(BeamParams P) {
           r.len = br.len + 1;
           r.last = i;
           r.flag = 0;
-          r.lmst = lm_next_state(P.lm, br.lmst, i);
+          r.lmst = lm_next_state(P.lm, br.lmst, i, &lmc);
           const int e = atomicAdd(&S.arena_used, 1);
           if (e < P.arena_cap) {
             arena[3 * e] = br.hist; arena[3 * e + 1] = i; arena[3 * e + 2] = t;
@@ -432,8 +446,16 @@ beam_search_kernel(BeamParams P) {
     hdr->n_beams = nb; hdr->position = t; hdr->arena_used = S.arena_used; hdr->error = S.error;
   }
   __syncthreads();
+  atomicAdd(&stat_cand, (unsigned long long)my_cand);
+  atomicAdd(&stat_probe, (unsigned long long)lmc.probes);
+  __syncthreads();
   if (P.finalize) {
-    if (tid == 0) P.out_n[2 * g] = nb, P.out_n[2 * g + 1] = S.error;
+    if (tid == 0) {
+      P.out_n[4 * g] = nb; P.out_n[4 * g + 1] = S.error;
+      // statistics of this launch: candidates scored and loads issued against the LM arrays (saturating int32)
+      P.out_n[4 * g + 2] = (int)(stat_cand > 0x7fffffffull ? 0x7fffffffull : stat_cand);
+      P.out_n[4 * g + 3] = (int)(stat_probe > 0x7fffffffull ? 0x7fffffffull : stat_probe);
+    }
     for (int r = tid; r < P.n_best; r += kBeamThreads) {
       const size_t o = (size_t)g * P.n_best + r;
       if (r < nb) {

@@ -85,7 +85,7 @@ class _Search:
         self.o_flag = torch.empty((self.n_seg, nb), dtype=torch.int32, device=self.dev)
         self.o_tok = torch.zeros((self.n_seg, nb, cap), dtype=torch.int32, device=self.dev)
         self.o_time = torch.zeros((self.n_seg, nb, cap), dtype=torch.int32, device=self.dev)
-        self.o_n = torch.zeros((self.n_seg, 2), dtype=torch.int32, device=self.dev)
+        self.o_n = torch.zeros((self.n_seg, 4), dtype=torch.int32, device=self.dev)
 
     def advance(self, n_frames, finalize=True):
         a = self.arr
@@ -119,6 +119,11 @@ class _Search:
                                   f"{_C.lib().dae_error_string(code).decode()} (more than 4096 candidates in one frame: "
                                   "lower beam_width or raise top_am_threshold)")
             return
+
+    def stats(self):
+        """(candidates scored, loads against the LM arrays) of the last launch, summed over segments."""
+        s = self.o_n[:, 2:4].to(torch.int64).sum(0).cpu().tolist()
+        return {"candidates": int(s[0]), "lm_loads": int(s[1])}
 
     def results(self):
         """-> per segment: list of (score, tokens, times, blank_end), best first."""

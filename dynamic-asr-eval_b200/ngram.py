@@ -180,6 +180,53 @@ class NGramLM:
         order, grams = read_arpa(path, word_to_id, bos_token(vocab_size, bos_id))
         return cls(grams, order, vocab_size, bos_id, unk_logprob10, device=device)
 
+    @classmethod
+    def synthetic(cls, vocab_size, order, last_level_nodes, seed=4, bos_id=0):
+        """A large random but well-formed LM built directly as trie arrays (no ARPA text, no python dict): every
+        context of fewer than ``order-1`` tokens over ids 0..V-1 exists (a full V-ary tree, so every fail link
+        does too) and ``last_level_nodes`` random n-grams of the highest order hang below it.  For benchmarks that
+        need a trie larger than L2 (bench.py); scoring semantics are those of the class docstring."""
+        V, rng = int(vocab_size), np.random.default_rng(seed)
+        self = cls.__new__(cls)
+        self.order, self.vocab_size, self.bos_id, self.bos_tok = int(order), V, int(bos_id), bos_token(V, bos_id)
+        self.device, self.unk_lp, self._dev, self._ids = None, np.float32(-10.0 * LN10), {}, None
+        full_depth = order - 1
+        level_start = [0]
+        for k in range(full_depth + 1):
+            level_start.append(level_start[-1] + V ** k)            # nodes of depth k occupy [start[k], start[k+1])
+        n_full = level_start[-1]
+        # last level: a sorted random sample of (parent at full_depth, token) pairs
+        n_par = V ** full_depth
+        pairs = np.unique(rng.integers(0, n_par * V, size=int(last_level_nodes * 1.05), dtype=np.int64))[:last_level_nodes]
+        n = n_full + len(pairs)
+        tok = np.zeros(n, np.int32); depth = np.zeros(n, np.int32); fail = np.zeros(n, np.int32)
+        cb = np.zeros(n + 1, np.int32)
+        for k in range(1, full_depth + 1):
+            idx = np.arange(V ** k, dtype=np.int64)                  # position inside level k = base-V digits t1..tk
+            tok[level_start[k]:level_start[k + 1]] = (idx % V).astype(np.int32)
+            depth[level_start[k]:level_start[k + 1]] = k
+            fail[level_start[k]:level_start[k + 1]] = (level_start[k - 1] + idx % (V ** (k - 1))).astype(np.int32)
+        tok[n_full:] = (pairs % V).astype(np.int32)
+        depth[n_full:] = order
+        par_pos = pairs // V
+        fail[n_full:] = (level_start[full_depth] + (par_pos % (V ** (full_depth - 1))) * V + pairs % V).astype(np.int32) \
+            if full_depth >= 1 else 0
+        # child runs: full levels have exactly V children each; the deepest full level gets the sampled runs
+        for k in range(full_depth):
+            cnt_idx = np.arange(V ** k, dtype=np.int64)
+            cb[level_start[k]:level_start[k + 1]] = (level_start[k + 1] + cnt_idx * V).astype(np.int32)
+        counts = np.bincount(par_pos, minlength=n_par)
+        cb[level_start[full_depth]:level_start[full_depth + 1]] = (n_full + np.concatenate(([0], np.cumsum(counts)[:-1]))).astype(np.int32)
+        cb[n_full:] = n
+        cb[n] = n
+        self.tok, self.depth, self.fail, self.cb, self.n_nodes = tok, depth, fail, cb, n
+        self.logp = (rng.uniform(-4.0, -0.05, size=n) * LN10).astype(np.float32)
+        self.bo = (rng.uniform(-1.0, -0.02, size=n) * LN10).astype(np.float32)
+        self.logp[0] = 0.0
+        self.bo[n_full:] = 0.0
+        self._level_start, self._full_depth = level_start, full_depth
+        return self
+
     # ---- LanguageModel duck type (lcasr/ctc_beam_search.py:45-87) -------------------------------------------
     # The "KV cache" of the reference is the token history here: state = {'cache': float32 [1,1,B,1,N,1] holding
     # the LM sequence of every beam (what BeamSearch.step pads, rearranges and slices, :284-312,172-191),
@@ -270,6 +317,12 @@ class NGramLM:
         """Trie node of the longest suffix of ``history`` (at most order-1 tokens) that is a node."""
         h = tuple(self.bos_tok if (t == self.bos_id and t != self.bos_tok) else t for t in history)
         h = h[-(self.order - 1):] if self.order > 1 else ()
+        if self._ids is None:                                       # synthetic(): full tree, positional index
+            h = tuple(t for t in h if 0 <= t < self.vocab_size)
+            pos = 0
+            for t in h:
+                pos = pos * self.vocab_size + t
+            return self._level_start[len(h)] + pos
         for s in range(len(h) + 1):
             j = self._ids.get(h[s:])
             if j is not None:

@@ -235,8 +235,10 @@ int dae_softdtw_bwd(const float* W, const float* gout, int64_t gout_stride, int 
  *              t_begin == 0 (re)initialises the search; otherwise it resumes from the stored position.
  * finalize     non-zero: write the n_best best beams of every segment:
  *              out_score/out_len/out_flag [n_seg, n_best], out_tok/out_time [n_seg, n_best, out_cap]
- *              (token ids and their start frames), out_n [n_seg, 2] = (number of live beams, error code:
- *              0, DAE_E_TOOBIG = more than 4096 candidates in one frame, DAE_E_SCRATCH = arena full).
+ *              (token ids and their start frames), out_n [n_seg, 4] = (number of live beams, error code:
+ *              0, DAE_E_TOOBIG = more than 4096 candidates in one frame, DAE_E_SCRATCH = arena full; candidates
+ *              scored in this launch; loads issued against the LM arrays in this launch — measured LM-probe
+ *              traffic = loads x 32-byte sectors).
  * ------------------------------------------------------------------------------------ */
 size_t dae_beam_scratch_bytes(int n_seg, int arena_cap);
 /* Dense expansion of the trie's context nodes (nodes 0..n_ctx-1, i.e. depth < order): row[s*vocab+w] =

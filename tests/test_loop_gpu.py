@@ -229,3 +229,37 @@ def test_adapt_on_concat_only_equals_return_params(cuda):
         outs.append(params)
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_cross_dataset_driver_matches_sequential_reference_flow(cuda, tmp_path):
+    """run_cross_dataset_eval (lcasr/run_cross_dataset_eval.py:96-212): baselines by `epochs=0`, adapt on A[i] with
+    return_params, evaluate on B and A leave-one-out, parameters restored; result schema as the reference pickles."""
+    import pickle
+    from types import SimpleNamespace
+    from dae import lib, run_cross_dataset_eval as x
+    from dae.optim import MADGRAD
+    from dae.standin import SyntheticTokenizer, synthetic_recordings
+    from dae.wer import rates_from_counts, word_error_counts
+    tok = SyntheticTokenizer(vocab_size=TOY["C"] - 1, seed=0)
+    data_a = synthetic_recordings("earnings22", tokenizer=tok, scale=0.0015)[:2]
+    data_b = synthetic_recordings("tedlium", tokenizer=tok, scale=0.003)[:2]
+    model = ToyModel(TOY["C"], seed=TOY["model_seed"])
+    save = str(tmp_path / "x.pkl")
+    args = SimpleNamespace(dataset="earnings22", dataset2="tedlium", repeats=1, save_path=save, seq_len=1024, overlap=512,
+                           adapt_overlap=None, awmc=False, config=TOY_CONFIG, **dict(TOY["kwargs"], epochs=1))
+    before = [p.detach().clone() for p in model.parameters()]
+    res = x.main(args, model, tok, data_a, data_b)[0]
+    assert all(torch.equal(a, b.to(a.device)) for a, b in zip(model.parameters(), before))
+    assert set(res) >= {"a_baseline", "b_baseline", "a_to_b", "a_to_a_loo", "dataset_a", "dataset_b", "args_dict", "repeat"}
+    assert len(res["a_to_b"]) == 2 and len(res["a_to_a_loo"]) == 2
+    assert pickle.load(open(save.replace(".pkl", "_1.pkl"), "rb"))["a_baseline"] == res["a_baseline"]
+    # the b baseline equals plain epochs=0 inference on every B recording
+    base = SimpleNamespace(**dict(vars(args), epochs=0))
+    hyp, gold = [], []
+    for r in data_b:
+        spec, g_ = r["process_fn"](r)
+        hyp.append(tok.decode(lib.dynamic_eval(base, model, spec, 1024, 512, tok, use_tqdm=False, optim=MADGRAD,
+                                               output="greedy")).lower())
+        gold.append(g_)
+    assert rates_from_counts(word_error_counts(hyp, gold))[0] == res["b_baseline"]["wer"]
+    assert res["a_to_b"][0]["words"] == res["b_baseline"]["words"]

@@ -130,3 +130,26 @@ def test_softdtw_module_normalize_and_errors(cuda):
     np.testing.assert_allclose(v, ref, rtol=1e-3, atol=1e-3)
     with pytest.raises(C.DaeError):
         SoftDTW(True)(X, Y)
+
+
+@pytest.mark.gpu
+def test_teacher_student_softdtw_loss_matches_oracle(cuda):
+    """The soft-DTW consumer sketched at wav2vec2/lib.py:184-191: loss value and the gradient reaching the student
+    posteriors against the fp64 oracle (E from softdtw_oracle.c, chained through the distance in torch fp64)."""
+    from dae.softdtw_loss import teacher_student_softdtw_loss
+    g = torch.Generator().manual_seed(17)
+    post = (torch.randn(3, 90, 24, generator=g) * 1.5).log_softmax(-1)            # 2 students + teacher
+    x = post.to(cuda).requires_grad_()
+    loss = teacher_student_softdtw_loss(x, gamma=1.5)
+    loss.backward()
+    xd = post.double().requires_grad_()
+    teacher, students = xd[-1].detach().unsqueeze(0).repeat(2, 1, 1), xd[:2]
+    D = ((teacher[:, :, None, :] - students[:, None, :, :]) ** 2).sum(-1)          # soft_dtw_cuda.py:319-329
+    R = so.forward(D.detach().numpy(), 1.5, 0.0)
+    E = so.backward(D.detach().numpy(), R, 1.5, 0.0)
+    ref = R[:, -2, -2].mean()
+    (torch.from_numpy(E) * D).sum().div(2).backward()                              # d loss / d students via E
+    assert abs(loss.item() - ref) <= 1e-5 * abs(ref)
+    assert x.grad[-1].abs().max().item() == 0                                      # the teacher row is detached
+    np.testing.assert_allclose(x.grad[:2].cpu().numpy(), xd.grad[:2].numpy(), rtol=1e-4,
+                               atol=1e-5 * float(xd.grad.abs().max()))

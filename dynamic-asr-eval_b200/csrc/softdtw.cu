@@ -70,13 +70,17 @@ __device__ __forceinline__ void cp_async4s(void* dst, const void* src) {
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+// Hand-over words between bands: GPU-scope relaxed accesses (L2 is the point of coherence between SMs).  `.volatile`
+// compiles to system-scope STRONG.SYS loads/stores, whose visibility latency is far longer; the tag lives in the
+// same 8-byte word as the value, so no ordering against other accesses is needed and the stores carry no memory
+// clobber (the compiler may schedule them freely among the chain's shared-memory traffic).
 __device__ __forceinline__ int2 ld_volatile_int2(const int2* p) {
   int2 v;
-  asm volatile("ld.volatile.global.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_volatile_int2(int2* p, int2 v) {
-  asm volatile("st.volatile.global.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+  asm volatile("st.relaxed.gpu.global.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y));
 }
 __device__ __forceinline__ float ex2f_(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float lg2f_(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }

@@ -160,6 +160,7 @@ struct BeamSmem {
   float c_score[kMaxCand];
   float c_final[kMaxCand];
   int sv[kMaxCand];
+  int rk_cum[257];                          // bucket starts
   unsigned char c_lead[kMaxCand];
   float red_f[kBeamThreads / 32];
   float red_g[kBeamThreads / 32];
@@ -396,15 +397,79 @@ beam_search_kernel(BeamParams P) {
     if (tid == 0) S.n_unflagged = 0;
     __syncthreads();
     BeamRec* nxt = S.next_beams;
-    // rank by (score desc, creation index asc); rank < beam_width survives at position rank
+    // rank by (score desc, creation index asc); rank < beam_width survives at position rank.  Large frames first
+    // sort the survivors into 256 score buckets (bucket index is monotone in the score, equal scores share a bucket),
+    // so a survivor's rank is the population of the better buckets plus an exact count inside its own bucket, and
+    // survivors whose better buckets already hold beam_width entries are dropped without any comparison.
+    const bool bucketed = nsv > 128;                       // CTA-uniform
+    int* sv2 = reinterpret_cast<int*>(S.c_score);          // survivors grouped by bucket (c_score is dead after P4)
+    if (bucketed) {
+      float lo = lim;
+      if (!P.has_prune) {                                  // no relative prune: the range is best - min
+        float mnv = CUDART_INF_F;
+        for (int j = tid; j < nsv; j += kBeamThreads) mnv = fminf(mnv, S.c_final[S.sv[j]]);
+        mnv = -warp_max(-mnv);
+        if (lane == 0) S.red_g[warp] = mnv;
+        __syncthreads();
+        lo = S.red_g[0];
+        for (int w = 1; w < kBeamThreads / 32; ++w) lo = fminf(lo, S.red_g[w]);
+      }
+      const float range = __fsub_rn(S.best, lo);
+      const float scale = (range > 0.0f && range < CUDART_INF_F) ? 256.0f / range : 0.0f;
+      for (int i = tid; i < kBtSlots; i += kBeamThreads) S.bt[i] = 0;        // [0,256) histogram, [256,512) cursors
+      __syncthreads();
+      for (int j = tid; j < nsv; j += kBeamThreads) {
+        const int c = S.sv[j];
+        int b = (int)(__fsub_rn(S.best, S.c_final[c]) * scale);
+        b = b < 0 ? 0 : (b > 255 ? 255 : b);
+        S.c_lead[c] = (unsigned char)b;                    // the leader flags are no longer needed
+        atomicAdd(&S.bt[b], 1);
+      }
+      __syncthreads();
+      {                                                    // exclusive scan of the 256 bucket counts
+        const int v = S.bt[tid];
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int n_ = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += n_;
+        }
+        if (lane == 31) S.warp_cnt[warp] = incl;
+        __syncthreads();
+        int off = 0;
+        for (int w = 0; w < warp; ++w) off += S.warp_cnt[w];
+        S.rk_cum[tid] = off + incl - v;
+        if (tid == kBeamThreads - 1) S.rk_cum[256] = off + incl;
+      }
+      __syncthreads();
+      for (int j = tid; j < nsv; j += kBeamThreads) {
+        const int c = S.sv[j];
+        const int b = S.c_lead[c];
+        sv2[S.rk_cum[b] + atomicAdd(&S.bt[256 + b], 1)] = c;
+      }
+      __syncthreads();
+    }
     for (int j = tid; j < nsv; j += kBeamThreads) {
       const int c = S.sv[j];
       const float f = S.c_final[c];
       int rank = 0;
-      for (int l = 0; l < nsv; ++l) {
-        const int c2 = S.sv[l];
-        const float f2 = S.c_final[c2];
-        rank += (f2 > f) || (f2 == f && c2 < c);
+      if (bucketed) {
+        const int b = S.c_lead[c];
+        rank = S.rk_cum[b];
+        if (rank < P.beam_width) {
+          const int hi = S.rk_cum[b + 1];
+          for (int l = S.rk_cum[b]; l < hi; ++l) {
+            const int c2 = sv2[l];
+            const float f2 = S.c_final[c2];
+            rank += (f2 > f) || (f2 == f && c2 < c);
+          }
+        }
+      } else {
+        for (int l = 0; l < nsv; ++l) {
+          const int c2 = S.sv[l];
+          const float f2 = S.c_final[c2];
+          rank += (f2 > f) || (f2 == f && c2 < c);
+        }
       }
       if (rank < P.beam_width) {
         const int b = c / ntop, k = c - b * ntop;

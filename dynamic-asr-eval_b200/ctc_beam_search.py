@@ -176,7 +176,7 @@ class BeamSearch:
         self.language_model = language_model
         self.blank_id = blank_id
         self.alpha, self.beta = alpha, beta
-        self.beams = []
+        self._beams, self._stale = [], False
         self.position = 0
         self.blank_penalty, self.repitition_penalty = blank_penalty, repitition_penalty
         self.top_am_threshold, self.prune_less_than_val = top_am_threshold, prune_less_than_val
@@ -196,7 +196,21 @@ class BeamSearch:
     def _refresh(self):
         res = self._s.results()[0]
         lm = self.language_model
-        self.beams = [Beam(sc, tok, tim, fl, lm.bos_id, self.blank_id) for sc, tok, tim, fl in res]
+        self._beams = [Beam(sc, tok, tim, fl, lm.bos_id, self.blank_id) for sc, tok, tim, fl in res]
+        self._stale = False
+
+    @property
+    def beams(self):
+        """Current hypotheses, best first (ctc_beam_search.py:118).  After step() they are only materialised (one
+        zero-frame launch that writes the n-best lists + the device-to-host copies) when somebody looks."""
+        if self._stale:
+            self._s.advance(0, finalize=True)
+            self._refresh()
+        return self._beams
+
+    @beams.setter
+    def beams(self, value):
+        self._beams, self._stale = value, False
 
     def run_search(self, use_tqdm=True):
         s = self._search()
@@ -211,8 +225,8 @@ class BeamSearch:
         s = self._search()
         if self.position == s.max_T:
             return False
-        s.advance(1, finalize=True)
-        self._refresh()
+        s.advance(1, finalize=False)                        # the search state stays on the device
+        self._stale = True
         if self.position == s.max_T - 1:                   # ctc_beam_search.py:280-282: last frame, stay there
             self.position = s.max_T
             return False
@@ -220,10 +234,11 @@ class BeamSearch:
         return True
 
     def return_text(self, idx):
-        if idx >= len(self.beams):
+        beams = self.beams
+        if idx >= len(beams):
             print('Beam index out of range')
             return
-        return self.tokenizer.decode(self.beams[idx].lm_sequence[1:])
+        return self.tokenizer.decode(beams[idx].lm_sequence[1:])
 
     def print_beams(self):
         for i, beam in enumerate(self.beams):

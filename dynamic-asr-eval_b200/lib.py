@@ -285,7 +285,7 @@ def dynamic_eval_ctc_loss(
             if d.get('_record_steps', False):
                 step_log.append({'key': i, 'ids': ids, 'loss': loss.detach()})   # no sync here
             if online:
-                kept[i] = (post[-1].detach(), u_len)
+                kept[i] = (post[-1].detach().clone(), u_len)   # a copy: a view would pin the whole [2,T',C] batch
         tm.add('adapt', time.perf_counter() - e0)
         if print_runtimes:
             torch.cuda.synchronize(device)

@@ -32,7 +32,7 @@ __device__ __forceinline__ void argmax_rows(const float* __restrict__ lp, int64_
     int bi = 0x7fffffff;
     if (VEC) {
       const int n4 = C >> 2;
-      constexpr int U = 8;
+      constexpr int U = 16;                                // 8 KB of loads in flight per warp
       int j = lane;
       for (; j + 32 * (U - 1) < n4; j += 32 * U) {
         float4 v[U];
@@ -193,8 +193,7 @@ extern "C" int dae_greedy_collapse(const float* lp, int64_t sB, int64_t sT, int 
   if (T > 0 && scratch) {
     // fused single launch; two CTAs of 16 warps per SM keep ~128 KB of loads in flight per SM
     const int64_t nrows = (int64_t)B * T;
-    const int64_t want = (nrows + 15) / 16;
-    const int grid = (int)(want < (int64_t)kNumSMs * 2 ? want : (int64_t)kNumSMs * 2);
+    const int grid = (int)(nrows < (int64_t)kNumSMs * 2 ? nrows : (int64_t)kNumSMs * 2);   // round-robin rows: equal bytes per SM
     const bool vec = aligned16(lp) && (C % 4 == 0) && (sT % 4 == 0) && (sB % 4 == 0);
     unsigned int* counter = (unsigned int*)scratch;
     if (vec)

@@ -170,7 +170,40 @@ specaug_premean_kernel(const float* __restrict__ x, int64_t sF, int F, int T, co
   const int64_t plane = (int64_t)F * T;
   const int t4 = T >> 2;
   const int64_t n_items = VEC ? (int64_t)F * t4 : plane;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_items; i += (int64_t)gridDim.x * 256) {
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  if (VEC) {
+    // two items per iteration: both loads are issued before either is used
+    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < n_items; i0 += 2 * stride) {
+      const int64_t i1 = i0 + stride;
+      const int f0 = (int)(i0 / t4), c0 = 4 * (int)(i0 - (int64_t)f0 * t4);
+      const bool has1 = i1 < n_items;
+      const int f1 = has1 ? (int)(i1 / t4) : f0, c1 = has1 ? 4 * (int)(i1 - (int64_t)f1 * t4) : c0;
+      const float4 va = ld_stream4(x + f0 * sF + c0);
+      const float4 vb = ld_stream4(x + f1 * sF + c1);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !has1) break;
+        const int f = u ? f1 : f0, c = u ? c1 : c0;
+        const float4 v = u ? vb : va;
+        const int64_t o = (int64_t)f * T + c;
+        for (int a = 0; a < bands.n_aug; ++a) {
+          float4 m = v;
+          if (in_bands(bands.f[a], bands.nf, f)) {
+            m = make_float4(fill, fill, fill, fill);
+          } else if (bands.nt) {
+            if (in_bands(bands.t[a], bands.nt, c)) m.x = fill;
+            if (in_bands(bands.t[a], bands.nt, c + 1)) m.y = fill;
+            if (in_bands(bands.t[a], bands.nt, c + 2)) m.z = fill;
+            if (in_bands(bands.t[a], bands.nt, c + 3)) m.w = fill;
+          }
+          st_stream4(out + a * plane + o, m);
+        }
+        for (int k = 0; k < n_clean; ++k) st_stream4(out + (bands.n_aug + k) * plane + o, v);
+      }
+    }
+    return;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_items; i += stride) {
     if (VEC) {
       const int f = (int)(i / t4), c = 4 * (int)(i - (int64_t)f * t4);
       const float4 v = ld_stream4(x + f * sF + c);
@@ -237,8 +270,8 @@ extern "C" int dae_specaug_repeat_premean(const float* x, int64_t sF, int F, int
   if (n_aug + n_clean == 0) return 0;
   const bool vec = aligned16(x) && aligned16(out) && (T % 4 == 0) && (sF % 4 == 0);
   const int64_t n_items = vec ? (int64_t)F * (T >> 2) : (int64_t)F * T;
-  int64_t want = (n_items + 255) / 256;
-  const int grid = (int)(want < (int64_t)kNumSMs * 8 ? want : (int64_t)kNumSMs * 8);
+  int64_t want = (n_items + 511) / 512;                   // two items per thread and iteration
+  const int grid = (int)(want < (int64_t)kNumSMs * 4 ? want : (int64_t)kNumSMs * 4);
   const int zm = (zero_masking || n_aug == 0) ? 1 : 0;
   if (vec)
     specaug_premean_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, sF, F, T, win_sums, zm, n_clean, bs, out, mean_out);

@@ -7,7 +7,7 @@ TAG=${1:-r01}; shift
 FAMS=${@:-ctc greedy specaug stitch softdtw beam}
 O=gpurun_out
 mkdir -p $O
-KRE='regex:ctc_|argmax_rows|collapse_kernel|specaug_|stitch_kernel|softdtw_|beam_search|cutout_|ngram_'
+KRE='regex:ctc_|argmax_rows|collapse_kernel|greedy_fused|specaug_|window_sums|stitch_kernel|softdtw_|beam_search|cutout_|ngram_|frame_shuffle|noise_'
 for fam in $FAMS; do
   timeout 300 python tools/prof_one.py $fam --reps 2 > $O/plain_$fam.log 2>&1 || { echo "plain run of $fam failed"; tail -5 $O/plain_$fam.log; exit 1; }
 done

@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "dynamic-asr-eval_b200", "libdae.so")
-WATCH = ["UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "LDGSTS", "UCGABAR", "MUFU.EX2", "MUFU.LG2", "MUFU.RCP", "SHFL", "REDUX",
+WATCH = ["CREDUX", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "LDGSTS", "UCGABAR", "MUFU.EX2", "MUFU.LG2", "MUFU.RCP", "SHFL", "REDUX",
          "BAR.SYNC", "LDS", "STS", "LDG", "STG", "ATOM", "RED", "DADD", "DFMA", "DMUL", "FFMA", "FADD", "FMUL", "FMNMX",
          "HMMA", "UTC"]
 

@@ -69,10 +69,15 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+ONLINE = False      # --online: the configuration of the reference's only published timing (timeit_earnings22.sh:1)
+
+
 def make_args(config):
     from types import SimpleNamespace
     a = SimpleNamespace(config=config)
     a.__dict__.update(KW)
+    if ONLINE:
+        a.__dict__.update(online=True, spec_augment_freq_mask_param=10)
     a.__dict__["_record_steps"] = True        # per-window pseudo-label lengths (host ints, already on the host)
     return a
 
@@ -140,12 +145,14 @@ def run_reference(a, rank, world):
 
 
 def workload_config(a):
+    mode = ("online=True: 1 epoch in window order, teacher posteriors stitched, no final pass, 6 freq masks x 10 "
+            "(lcasr/launch_scripts/timeit_earnings22.sh:1)") if ONLINE else "1 epoch + final pass + stitch + greedy"
     return {"workload": f"dynamic eval of one synthetic Earnings22-shaped recording per step ({a.frames} frames = "
                         f"{a.frames / FPS / 60:.1f} min, 80-mel, seq {SEQ_LEN} overlap {OVERLAP}, "
-                        f"{n_windows(a.frames)} windows, 1 epoch + final pass + stitch + greedy)",
+                        f"{n_windows(a.frames)} windows, {mode})",
             "standin_encoder": "lcasr160rb1-shaped (6 layers, d=768, 6x128 heads, conv k=9, x8 subsampling, C=4096), "
                                "fp32, random-init, PyTorch (not the product)",
-            "spec_augment": "6 freq masks x 34, 0 time masks", "optimizer": "MADGRAD lr 9e-5",
+            "spec_augment": ("6 freq masks x 10" if ONLINE else "6 freq masks x 34") + ", 0 time masks", "optimizer": "MADGRAD lr 9e-5",
             "l2": "inputs larger than L2 (model weights 0.36 GB + activations stream through every step)",
             "parallelism": f"recordings sharded over {a.gpus} rank(s), one int64[5] all-reduce per step"}
 
@@ -615,6 +622,8 @@ def main():
     ap.add_argument("--impl", default="dae", choices=["dae", "reference"])
     ap.add_argument("--frames", type=int, default=120000, help="frames per synthetic recording (100 fps)")
     ap.add_argument("--no-aux", dest="no_aux", action="store_true", help="skip the BASELINE-shape kernel table")
+    ap.add_argument("--online", action="store_true",
+                    help="online=True + freq_mask_param 10: the reference's published-timing configuration")
     ap.add_argument("--sweep", default="", choices=["", "tedlium", "rev16", "earnings22"],
                     help="strong-scaling sweep over a fixed ragged recording set (BASELINE.json configs[4])")
     ap.add_argument("--sweep-scale", dest="sweep_scale", type=float, default=1.0, help="shrink the sweep's durations")
@@ -622,6 +631,8 @@ def main():
                     help="--impl reference: where the stand-in encoder + torch CTC run (cpu = host cores, the "
                          "contract's arm; cuda = the reference's real placement, lcasr/lib.py:549)")
     a = ap.parse_args()
+    global ONLINE
+    ONLINE = bool(a.online)
     if a.impl == "reference":
         run_reference(a, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return

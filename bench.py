@@ -248,6 +248,8 @@ def aux_kernels(peak):
     lps = torch.from_numpy(peaky_log_probs(T, V + 1, V, 3, sharp=12.0)).cuda()
     beam_case("beam_search[360 segments, speech-like sharp posteriors]", lps, lm, True, offs,
               "top class ~0.99 per frame (sharp=12), as trained CTC models emit: 1-3 candidate classes per frame")
+    beam_case("beam_search[1h, one sequence, speech-like sharp posteriors]", lps, lm, True, [0, T],
+              "per-frame latency of ONE search on speech-like posteriors")
     return out
 
 

@@ -9,7 +9,7 @@ from ctypes import c_char_p, c_int, c_int32, c_int64, c_size_t, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdae.so")
+LIB_PATH = os.environ.get("DAE_LIBDAE") or os.path.join(_HERE, "libdae.so")   # override: A/B builds of the library
 
 
 class DaeError(RuntimeError):

@@ -39,7 +39,13 @@ constexpr int kBand = 32;                 // rows per warp
 constexpr int kTile = 32;                 // columns per staged tile
 // columns per export poll group: the group head (poll, prefetch, smem reads) is amortised over the group, the band
 // below trails by a few more steps
-constexpr int kGrpFwd = 8, kGrpBwd = 16;
+#ifndef DAE_SDTW_GF
+#define DAE_SDTW_GF 8
+#endif
+#ifndef DAE_SDTW_GB
+#define DAE_SDTW_GB 16
+#endif
+constexpr int kGrpFwd = DAE_SDTW_GF, kGrpBwd = DAE_SDTW_GB;
 constexpr double kLog2e = 1.4426950408889634;
 constexpr double kLn2 = 0.6931471805599453;
 
@@ -294,8 +300,8 @@ softdtw_fwd_kernel(SdtwParams P, int vec, int smem_per_warp) {
           const int col = p + lane;
           const bool need_v = lane < kGrp && col < M;
           const bool need = need_v || lane == kGrp;
-          const int want = need_v ? col + 1 : (p >> 3) + 1;
-          const int2* addr = need_v ? (exp_up + col) : (mu_up_p + (p >> 3));
+          const int want = need_v ? col + 1 : (p / kGrp) + 1;
+          const int2* addr = need_v ? (exp_up + col) : (mu_up_p + (p / kGrp));
           int2 w = nx;
           for (;;) {
             if (__all_sync(0xffffffffu, !need || w.y == want)) break;
@@ -306,7 +312,7 @@ softdtw_fwd_kernel(SdtwParams P, int vec, int smem_per_warp) {
           ab_v = __int_as_float(w.x) + (mu_pub - mu);        // exact integer shift between the two frames
           const int col2 = col + kGrp;
           if (lane < kGrp && col2 < M) nx = ld_volatile_int2(exp_up + col2);
-          else if (lane == kGrp && p + kGrp < M) nx = ld_volatile_int2(mu_up_p + ((p + kGrp) >> 3));
+          else if (lane == kGrp && p + kGrp < M) nx = ld_volatile_int2(mu_up_p + ((p + kGrp) / kGrp));
         }
         // shift for the re-centring at the last step of this group: follows the minimum over the active lanes
         float shift;
@@ -357,7 +363,7 @@ softdtw_fwd_kernel(SdtwParams P, int vec, int smem_per_warp) {
             const int jq = j - kGrp + q;
             if ((unsigned)jq < (unsigned)M) {
               st_volatile_int2(exp_mine + jq, make_int2(__float_as_int(pub[q]), jq + 1));
-              if (q == kGrp - 1) st_volatile_int2(mu_mine + (jq >> 3), make_int2(__float_as_int(mu), (jq >> 3) + 1));
+              if (q == kGrp - 1) st_volatile_int2(mu_mine + (jq / kGrp), make_int2(__float_as_int(mu), (jq / kGrp) + 1));
             }
           }
         }
@@ -513,7 +519,7 @@ softdtw_bwd_kernel(SdtwParams P, int vec, int smem_per_warp) {
 static size_t sdtw_scratch(int B, int N, int M) {
   const size_t nb = (size_t)(N + kBand - 1) / kBand;
   const size_t Mp = ((size_t)M + 3) / 4 * 4;
-  const size_t Mg = ((size_t)M + 7) / 8 + 1;
+  const size_t Mg = ((size_t)M + kGrpFwd - 1) / kGrpFwd + 1;
   return 256 + (size_t)B * nb * (Mp + Mg) * sizeof(int2);
 }
 
@@ -531,7 +537,7 @@ static int softdtw_setup(dae::SdtwParams& P, int B, int N, int M, void* scratch,
   P.B = B; P.N = N; P.M = M;
   P.nbands = (N + kBand - 1) / kBand;
   P.Mp = (M + 3) / 4 * 4;
-  P.Mg = (M + 7) / 8 + 1;
+  P.Mg = (M + kGrpFwd - 1) / kGrpFwd + 1;
   P.ticket = reinterpret_cast<int*>(scratch);
   P.exp_buf = reinterpret_cast<int2*>(reinterpret_cast<char*>(scratch) + 256);
   P.exp_mu = P.exp_buf + (size_t)B * P.nbands * P.Mp;

@@ -141,6 +141,9 @@ def run_reference(a, rank, world):
         "config": workload_config(a),
         "cpu_baseline": {"value": val, "unit": "audio-hours/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "ONE host process on rank 0 whatever --gpus says (the contract of this arm): at N > 1 compare it with the "
+                "dae arm's value / N; the same loop with the encoder on the GPU (the reference's real placement) is the "
+                "dae arm's `gpu_reference_loop` key, or `--ref-device cuda` here",
     }), flush=True)
 
 

@@ -101,7 +101,7 @@ class SpecAugment(torch.nn.Module):
         nf, nt = int(fb.shape[1]), int(tb.shape[1])
         st = _C.stream_ptr(dev)
         with torch.cuda.device(dev), prof.span("specaug_repeat", (1 + B + n_clean) * F * T * 4):
-            if n_clean and window_sums is not None:
+            if window_sums is not None:
                 # the window's partial sums are known (SpecAugment.window_sums): one plain single-pass launch
                 src = x[0]
                 if src.stride(1) != 1:

@@ -8,10 +8,14 @@
 What changed underneath (same arithmetic, different placement):
   * the spectrogram is copied to the GPU once; windows are device views (the reference builds and
     augments every window on the CPU and copies [2,80,16384] per step, lib.py:538-549);
-  * SpecAugment + the ``repeat(2,1,1)`` batch build is one kernel pair (dae_specaug_repeat);
+  * the reference runs [augmented, clean] as ONE batch with autograd on (lib.py:539-550) although the loss only
+    sees the augmented row (:570); here the clean (teacher) branch runs first without a graph and the augmented
+    branch alone carries the gradient: same parameter gradient (the clean row's upstream gradient is exactly
+    zero), one third less encoder work per step (``split_branches=False`` restores the single batched call);
+  * SpecAugment masks straight from the window view (per-recording window sums + one single-pass launch);
   * pseudo-labels come from the greedy kernel on the device posteriors; only the collapsed ids
     cross PCIe for the tokenizer's decode -> re-encode round trip (lib.py:559,569 copy 33.5 MB
-    twice per step to the host);
+    twice per step to the host), and that hop runs while the GPU computes the augmented branch;
   * CTC loss/grad run in dae_ctc_lattice + dae_ctc_grad;
   * final-pass window posteriors stay on the device and are stitched by dae_stitch (the reference
     keeps ~6.6 GB of host copies and two ~2 GB host accumulators for a 69 min recording).

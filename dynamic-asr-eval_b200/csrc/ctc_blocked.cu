@@ -226,6 +226,8 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
   // Launched with programmatic stream serialization: everything above overlaps the band kernel's tail; its
   // results (bands, zeroed hand-over words, label groups) are visible from here on.
   cudaGridDependencySynchronize();
+  // every CTA of the scan is resident now: a dependent launch (ctc_dense_grad_kernel) may take the idle SMs
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (g >= sc.G) return;                                // grid padded to whole clusters
   const bool up_local = CL > 1 && crank > 0 && g > 0;
   const bool down_local = CL > 1 && crank + 1 < CL && g + 1 < sc.G;
@@ -778,7 +780,7 @@ __host__ __device__ inline BgSmem bg_smem_layout(int Lp, int Sp, int K) {
 //   2. occupancies 2^(alpha~ + beta~ + (offA + offB - ll2) - x) of every state of every row; per class sums by
 //      walking the first-occurrence lists (deterministic order), then the few classes that occur in the label
 //      sequence (and blank) are overwritten with g*(exp(lp) - occupancy).
-template <int P, int K, int MAXT, int MINB>
+template <int P, int K, int MAXT, int MINB, bool SPARSE>
 __global__ void __launch_bounds__(MAXT, MINB)
 ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, int C,
                       const int64_t* __restrict__ tgt, int64_t tgt_stride, int Lmax,
@@ -853,10 +855,12 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
   // end.  Otherwise:
   // half of the grid streams first and runs its chains later, the other half the other way round, so the two
   // CTAs that share an SM overlap memory traffic with the latency-bound chains
-  const bool table = vec && (size_t)KH * Cq <= (size_t)2 * K * lay.row_stride;
-  const bool dense_first = !table && ((int)blockIdx.x * 2 < (int)gridDim.x || kb == 0);
+  // SPARSE: ctc_dense_grad_kernel has written g*exp(lp) (and the zero rows) already, under the scan's shadow; only
+  // the classes of the label sequence and blank are left to do.
+  const bool table = !SPARSE && vec && (size_t)KH * Cq <= (size_t)2 * K * lay.row_stride;
+  const bool dense_first = !SPARSE && !table && ((int)blockIdx.x * 2 < (int)gridDim.x || kb == 0);
   if (kb == 0) {
-    dense();
+    if (!SPARSE) dense();
     return;
   }
 
@@ -1037,7 +1041,7 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
     }
   }
 
-  if (!dense_first && !table) dense();
+  if (!SPARSE && !dense_first && !table) dense();
   __syncthreads();                               // dense stores of every thread precede the sparse overwrite
 
   // ---- 2. occupancies and the sparse correction (gam: label emissions are replaced by label occupancies)
@@ -1131,12 +1135,12 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
   }
 }
 
-template <int P, int MAXT, int MINB>
+template <int P, int MAXT, int MINB, bool SPARSE>
 static int launch_block_grad(int NTc, cudaStream_t st, int N, const float* lp, int64_t sT, int64_t sN, int T, int C,
                              const int64_t* tgt, int64_t tgt_stride, int Lmax, const int64_t* in_len,
                              const int64_t* tgt_len, int blank, const float* gout, int64_t gout_stride, float* grad,
                              const CtcScratch& sc, const BgSmem& lay, int vec) {
-  auto kern = ctc_block_grad_kernel<P, kBlkK, MAXT, MINB>;
+  auto kern = ctc_block_grad_kernel<P, kBlkK, MAXT, MINB, SPARSE>;
   DAE_CUDA(ensure_dyn_smem(kern, lay.total));
   kern<<<dim3(sc.nblk, N), NTc, lay.total, st>>>(lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, gout,
                                                  gout_stride, grad, sc, lay, vec);
@@ -1149,23 +1153,99 @@ static int launch_block_grad(int NTc, cudaStream_t st, int N, const float* lp, i
 int ctc_blocked_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
                      int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank,
                      const float* gout, int64_t gout_stride, float* grad, const CtcScratch& sc, int vec,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool sparse_only) {
   int P, NTc;
   lat_geometry(Lmax, P, NTc);
   const BgSmem lay = bg_smem_layout(sc.Lp, sc.Sp, kBlkK);
   if (lay.total > 110 * 1024) {                  // two CTAs per SM or not at all
+    if (sparse_only) return DAE_E_TOOBIG;        // the caller checks ctc_split_fits first
     int rc = ctc_blocked_fill(lp, sT, sN, T, N, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, sc, st);
     return rc ? rc : 1;
   }
-#define DAE_BG(PP, MT, MB)                                                                                         \
-  return launch_block_grad<PP, MT, MB>(NTc, st, N, lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, \
-                                       gout, gout_stride, grad, sc, lay, vec)
+#define DAE_BG(PP, MT, MB)                                                                                          \
+  {                                                                                                                 \
+    if (sparse_only)                                                                                                \
+      return launch_block_grad<PP, MT, MB, true>(NTc, st, N, lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len,       \
+                                                 tgt_len, blank, gout, gout_stride, grad, sc, lay, vec);            \
+    return launch_block_grad<PP, MT, MB, false>(NTc, st, N, lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len,        \
+                                                tgt_len, blank, gout, gout_stride, grad, sc, lay, vec);             \
+  }
   constexpr int kMaxC = kLatThreads - 64;
   if (P <= 1 && NTc <= 640) DAE_BG(1, 640, 2);
   if (P <= 1) DAE_BG(1, kMaxC, 1);
   if (P <= 2) DAE_BG(2, kMaxC, 1);
   DAE_BG(4, kMaxC, 1);
 #undef DAE_BG
+}
+
+// ------------------------------------------------------------------------------------------ 5. split gradient
+// With the upstream scale known at loss time (dae_ctc_loss_grad) the class-dense part of the gradient, g*exp(lp),
+// does not have to wait for the scan: it is streamed by a kernel that starts as soon as every scan CTA is
+// resident (programmatic dependent launch; the scan releases its dependents right after its own wait) and runs
+// on the SMs the scan leaves idle.  The launch asks for more shared memory than an SM has left beside a scan CTA,
+// so no streaming CTA ever shares an SM (and issue slots) with the latency-bound scan.  Only the sparse part is
+// left for after the scan (ctc_block_grad_kernel<SPARSE>).
+constexpr int kDenseThreads = 1024;
+constexpr int kDenseRows = 4;                     // rows per unit: independent 128-bit loads in flight per thread
+constexpr int kDenseSmemReserve = 192 * 1024;     // + the scan CTA's >= 40 KB: does not fit in 227 KB
+constexpr int kScanCtasMax = 48;                  // the split path is taken when the scan leaves >= 100 SMs idle
+
+__global__ void __launch_bounds__(kDenseThreads, 1)
+ctc_dense_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, int N, int C,
+                      const int64_t* __restrict__ in_len, const float* __restrict__ gout, int64_t gout_stride,
+                      float* __restrict__ grad) {
+  constexpr int R = kDenseRows;
+  const int units_n = (T + R - 1) / R, C4 = C >> 2;
+  for (int unit = blockIdx.x; unit < units_n * N; unit += gridDim.x) {
+    const int n = unit / units_n, t0 = (unit - n * units_n) * R;
+    int Tn = (int)in_len[n];
+    Tn = Tn < 0 ? 0 : (Tn > T ? T : Tn);
+    const float g = gout[n * gout_stride];
+    const float* base = lp + n * sN + (int64_t)t0 * sT;
+    for (int i = threadIdx.x; i < C4; i += kDenseThreads) {
+      float4 v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (t0 + r < Tn) v[r] = __ldcs(reinterpret_cast<const float4*>(base + (int64_t)r * sT) + i);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (t0 + r < T) {
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t0 + r < Tn) o = make_float4(__expf(v[r].x) * g, __expf(v[r].y) * g, __expf(v[r].z) * g, __expf(v[r].w) * g);
+          // plain stores: the sparse pass overwrites a few hundred words of every row while it is still in L2
+          reinterpret_cast<float4*>(grad + ((int64_t)(t0 + r) * N + n) * C)[i] = o;
+        }
+      }
+    }
+  }
+  // completes only after the scan has: a later launch in the stream must not overtake the scan through this kernel
+  cudaGridDependencySynchronize();
+}
+
+bool ctc_split_fits(const CtcScratch& sc, int N, int vec) {
+  if (!sc.xfer || !vec) return false;
+  if (ctc_config().split.load(std::memory_order_relaxed) == 0) return false;
+  const BgSmem lay = bg_smem_layout(sc.Lp, sc.Sp, kBlkK);
+  const int cl = 8;
+  return lay.total <= 110 * 1024 && (sc.G + cl - 1) / cl * cl * 2 * N <= kScanCtasMax;
+}
+
+int ctc_blocked_dense(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* in_len,
+                      const float* gout, int64_t gout_stride, float* grad, cudaStream_t st) {
+  DAE_CUDA(ensure_dyn_smem(ctc_dense_grad_kernel, kDenseSmemReserve));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(148 - kScanCtasMax);
+  cfg.blockDim = dim3(kDenseThreads);
+  cfg.dynamicSmemBytes = kDenseSmemReserve;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DAE_CUDA(cudaLaunchKernelEx(&cfg, ctc_dense_grad_kernel, lp, sT, sN, T, N, C, in_len, gout, gout_stride, grad));
+  DAE_LAUNCH_OK();
+  return 0;
 }
 
 int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,

@@ -482,9 +482,13 @@ def run_dae(a, rank, world, local):
                        "algorithmic_bytes_per_launch": r["bytes_per_launch"],
                        "gbs": (r["bytes_per_launch"] / (r["avg_ms"] * 1e-3) / 1e9) if r["avg_ms"] > 0 else None}
     roof = None
-    if "ctc_lattice" in kern and "ctc_grad" in kern:
-        t_pair = kern["ctc_lattice"]["avg_ms"] + kern["ctc_grad"]["avg_ms"]
-        by = kern["ctc_grad"]["bytes_per_launch"]                 # 2*T*N*C*4: read lp once, write grad once
+    if "ctc_loss_grad" in kern or ("ctc_lattice" in kern and "ctc_grad" in kern):
+        if "ctc_loss_grad" in kern:                               # one library call: bands, scan, dense + sparse gradient
+            t_pair = kern["ctc_loss_grad"]["avg_ms"]
+            by = kern["ctc_loss_grad"]["bytes_per_launch"]
+        else:
+            t_pair = kern["ctc_lattice"]["avg_ms"] + kern["ctc_grad"]["avg_ms"]
+            by = kern["ctc_grad"]["bytes_per_launch"]             # 2*T*N*C*4: read lp once, write grad once
         ach = by / (t_pair * 1e-3) / 1e9
         traffic, traffic_warm = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -498,7 +502,7 @@ def run_dae(a, rank, world, local):
                                 "between kernels); with ncu --cache-control none the same launches move "
                                 f"{traffic_warm} bytes (bands/emissions stay in the 126 MB L2)",
                 "algorithmic_bytes": by, "peak_source": peak_src, "avg_launch_us": t_pair * 1e3,
-                "note": "N=1: time-blocked lattice (transfer bands + 256-step boundary scan + fused block gradient); the scan is a dependent chain (latency-bound); see DESIGN.md"}
+                "note": "N=1: time-blocked lattice (transfer bands + 256-step boundary scan; the dense part of the gradient streams under the scan, the label classes follow it); the scan is a dependent chain (latency-bound); see DESIGN.md"}
     cpu = cpu_baseline_sample(a.frames) if world == 1 else None
     aux = aux_kernels(peak) if (world == 1 and not a.no_aux) else None
     extra = {}

@@ -40,7 +40,10 @@ _PROTOS = {
     "dae_noise_scratch_bytes": (c_size_t, []),
     "dae_add_noise": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, ctypes.c_float, c_void_p, c_size_t,
                               c_void_p, c_void_p]),
-    "dae_ctc_configure": (None, [c_int, c_int, c_int]),
+    "dae_ctc_configure": (None, [c_int, c_int, c_int, c_int]),
+    "dae_ctc_loss_grad": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
+                                  c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                  c_void_p, c_size_t, c_void_p]),
     "dae_ctc_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dae_ctc_lattice": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
                                 c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -105,9 +108,9 @@ def require_cuda(t: torch.Tensor, name: str):
         raise DaeError(f"{name} must be a CUDA tensor: the dae kernels have no CPU path")
 
 
-def ctc_configure(blocked: int = -1, cluster: int = 0, pairs: int = 0):
+def ctc_configure(blocked: int = -1, cluster: int = 0, pairs: int = 0, overlap: int = -1):
     """Force the CTC lattice implementation (tests / tools): see dae_ctc_configure in include/dae.h."""
-    lib().dae_ctc_configure(int(blocked), int(cluster), int(pairs))
+    lib().dae_ctc_configure(int(blocked), int(cluster), int(pairs), int(overlap))
 
 
 def launch_count() -> int:

@@ -67,6 +67,9 @@ inline cudaError_t ensure_dyn_smem(Kern kern, int bytes) {
   return ensure_dyn_smem_impl(reinterpret_cast<const void*>(kern), bytes);
 }
 
+// SM count of the current device (cached per device; 0 on error).
+int sm_count();
+
 __host__ __device__ __forceinline__ bool aligned16(const void* p) {
   return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
 }

@@ -429,9 +429,9 @@ static int ctc_check(const float* lp, int T, int N, int C, const int64_t* tgt, i
   return 0;
 }
 
-extern "C" int dae_ctc_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
-                               int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len,
-                               int blank, float* nll, void* scratch, size_t scratch_bytes, void* stream) {
+static int ctc_lattice_impl(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
+                            int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank,
+                            float* nll, void* scratch, size_t scratch_bytes, void* stream, bool dense_follows) {
   using namespace dae;
   int rc = ctc_check(lp, T, N, C, tgt, Lmax, in_len, tgt_len, blank, scratch, scratch_bytes);
   if (rc) return rc;
@@ -441,7 +441,7 @@ extern "C" int dae_ctc_lattice(const float* lp, int64_t sT, int64_t sN, int T, i
   ctc_carve(sc, scratch, T, N, Lmax);
   if (sc.xfer)                                           // few samples, many frames: spread the time axis over the GPU
     return ctc_blocked_lattice(lp, sT, sN, T, N, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, nll, sc,
-                               (cudaStream_t)stream);
+                               (cudaStream_t)stream, dense_follows);
   int P, NTc;
   lat_geometry(Lmax, P, NTc);
   const int NT = NTc + 64;                               // consumers + two helper warps
@@ -454,6 +454,13 @@ extern "C" int dae_ctc_lattice(const float* lp, int64_t sT, int64_t sN, int T, i
   if (P <= 2) DAE_LAT(2);
   DAE_LAT(4);
 #undef DAE_LAT
+}
+
+extern "C" int dae_ctc_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
+                               int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len,
+                               int blank, float* nll, void* scratch, size_t scratch_bytes, void* stream) {
+  return ctc_lattice_impl(lp, sT, sN, T, N, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, nll, scratch,
+                          scratch_bytes, stream, false);
 }
 
 extern "C" int dae_ctc_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
@@ -485,6 +492,32 @@ extern "C" int dae_ctc_grad(const float* lp, int64_t sT, int64_t sN, int T, int 
                                                                 tgt_len, blank, gout, gout_stride, grad, sc, vec);
   DAE_LAUNCH_OK();
   return 0;
+}
+
+// Loss and gradient in one call, for callers that know the upstream gradient when they ask for the loss.
+extern "C" int dae_ctc_loss_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
+                                 int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len,
+                                 int blank, float* nll, const float* gout, int64_t gout_stride, float* grad,
+                                 void* scratch, size_t scratch_bytes, void* stream) {
+  using namespace dae;
+  if (!gout || !grad) return DAE_E_BADARG;
+  int rc = ctc_check(lp, T, N, C, tgt, Lmax, in_len, tgt_len, blank, scratch, scratch_bytes);
+  if (rc) return rc;
+  CtcScratch sc;
+  ctc_carve(sc, scratch, T, N, Lmax);
+  const int vec_g = aligned16(lp) && aligned16(grad) && (C % 4 == 0) && (sT % 4 == 0) && (sN % 4 == 0);
+  const bool split = N > 0 && T > 0 && ctc_split_fits(sc, N, vec_g);
+  rc = ctc_lattice_impl(lp, sT, sN, T, N, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, nll, scratch, scratch_bytes,
+                        stream, split);
+  if (rc || N == 0 || T == 0) return rc;
+  if (split) {
+    rc = ctc_blocked_dense(lp, sT, sN, T, N, C, in_len, gout, gout_stride, grad, (cudaStream_t)stream);
+    if (rc) return rc;
+    return ctc_blocked_grad(lp, sT, sN, T, N, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, gout, gout_stride, grad,
+                            sc, vec_g, (cudaStream_t)stream, true);
+  }
+  return dae_ctc_grad(lp, sT, sN, T, N, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, nll, gout, gout_stride, grad,
+                      scratch, scratch_bytes, stream);
 }
 
 namespace dae {

@@ -199,7 +199,7 @@ constexpr int kBndThreads = kTpd * kRegion + 96;  // consumers + band-prefetch, 
 template <int K>
 __global__ void __launch_bounds__(kBndThreads)
 ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len,
-                    float* __restrict__ nll, CtcScratch sc) {
+                    float* __restrict__ nll, CtcScratch sc, int release_dependents) {
   constexpr int W = 2 * K + 1, H = 2 * K, CH = (kRegion + H) * W;
   __shared__ __align__(128) float xs[kBndStages][CH];   // band rows of the states this region reads, per step
   __shared__ __align__(8) float buf[2][H + kRegion + 2];   // [halo of the region below (raw) | own region | dead cell, pad]
@@ -226,8 +226,9 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
   // Launched with programmatic stream serialization: everything above overlaps the band kernel's tail; its
   // results (bands, zeroed hand-over words, label groups) are visible from here on.
   cudaGridDependencySynchronize();
-  // every CTA of the scan is resident now: a dependent launch (ctc_dense_grad_kernel) may take the idle SMs
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // every CTA of the scan is resident now: the dependent launch that follows (ctc_dense_grad_kernel, which waits
+  // for this grid before it completes) may take the idle SMs
+  if (release_dependents) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (g >= sc.G) return;                                // grid padded to whole clusters
   const bool up_local = CL > 1 && crank > 0 && g > 0;
   const bool down_local = CL > 1 && crank + 1 < CL && g + 1 < sc.G;
@@ -1223,8 +1224,8 @@ ctc_dense_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
 }
 
 bool ctc_split_fits(const CtcScratch& sc, int N, int vec) {
-  if (!sc.xfer || !vec) return false;
-  if (ctc_config().split.load(std::memory_order_relaxed) == 0) return false;
+  if (!sc.xfer || !vec || sm_count() < 2 * kScanCtasMax) return false;
+  if ((ctc_config().overlap.load(std::memory_order_relaxed) & 1) == 0) return false;
   const BgSmem lay = bg_smem_layout(sc.Lp, sc.Sp, kBlkK);
   const int cl = 8;
   return lay.total <= 110 * 1024 && (sc.G + cl - 1) / cl * cl * 2 * N <= kScanCtasMax;
@@ -1234,7 +1235,7 @@ int ctc_blocked_dense(const float* lp, int64_t sT, int64_t sN, int T, int N, int
                       const float* gout, int64_t gout_stride, float* grad, cudaStream_t st) {
   DAE_CUDA(ensure_dyn_smem(ctc_dense_grad_kernel, kDenseSmemReserve));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(148 - kScanCtasMax);
+  cfg.gridDim = dim3(sm_count() - kScanCtasMax);
   cfg.blockDim = dim3(kDenseThreads);
   cfg.dynamicSmemBytes = kDenseSmemReserve;
   cfg.stream = st;
@@ -1250,7 +1251,7 @@ int ctc_blocked_dense(const float* lp, int64_t sT, int64_t sN, int T, int N, int
 
 int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
                         int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank,
-                        float* nll, const CtcScratch& sc, cudaStream_t st) {
+                        float* nll, const CtcScratch& sc, cudaStream_t st, bool dense_follows) {
   (void)C;
   const int tiles = (sc.Sq + kXferTile - 1) / kXferTile;
   ctc_xfer_kernel<kBlkK><<<dim3(sc.nblk, tiles, N), kXferTile, 0, st>>>(lp, sT, sN, T, tgt, tgt_stride, Lmax, in_len,
@@ -1279,7 +1280,7 @@ int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, i
     cfg.numAttrs = 2;
     if (cfg.dynamicSmemBytes > 24 * 1024)
       DAE_CUDA(ensure_dyn_smem(ctc_boundary_kernel<kBlkK>, (int)cfg.dynamicSmemBytes));
-    DAE_CUDA(cudaLaunchKernelEx(&cfg, ctc_boundary_kernel<kBlkK>, T, Lmax, in_len, tgt_len, nll, sc));
+    DAE_CUDA(cudaLaunchKernelEx(&cfg, ctc_boundary_kernel<kBlkK>, T, Lmax, in_len, tgt_len, nll, sc, dense_follows ? 1 : 0));
     DAE_LAUNCH_OK();
   }
   return 0;

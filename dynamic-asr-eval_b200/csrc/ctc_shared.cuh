@@ -41,8 +41,9 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 // Thread geometry of the lattice kernel: P state pairs per consumer thread, NTc consumer threads.
 // Every consumer thread owns real or dummy pairs, so lattice rows are 2*NTc*P floats wide.
 // Path overrides (dae_ctc_configure): process-wide, read with relaxed atomics on every call; the environment
-// variables DAE_CTC_BLOCKED / DAE_CTC_CLUSTER / DAE_CTC_PAIRS only seed them once, when the library is first used.
-struct CtcConfig { std::atomic<int> blocked{-1}, cluster{0}, pairs{0}; };
+// variables DAE_CTC_BLOCKED / DAE_CTC_CLUSTER / DAE_CTC_PAIRS / DAE_CTC_OVERLAP only seed them once, when the library
+// is first used.  overlap: bit 0 = dae_ctc_loss_grad streams the dense gradient under the scan; -1 = all on.
+struct CtcConfig { std::atomic<int> blocked{-1}, cluster{0}, pairs{0}, overlap{-1}; };
 CtcConfig& ctc_config();
 
 static inline void lat_geometry(int Lmax, int& P, int& NTc) {
@@ -163,7 +164,7 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
 // ctc_blocked.cu: fills the same scratch (alpha, beta_rev, offsets, label groups, ll2) and nll as ctc_lattice_kernel.
 int ctc_blocked_lattice(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
                         int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank,
-                        float* nll, const CtcScratch& sc, cudaStream_t st);
+                        float* nll, const CtcScratch& sc, cudaStream_t st, bool dense_follows = false);
 
 int ctc_blocked_fill(const float* lp, int64_t sT, int64_t sN, int T, int N, const int64_t* tgt, int64_t tgt_stride,
                      int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank, const CtcScratch& sc,
@@ -172,6 +173,10 @@ int ctc_blocked_fill(const float* lp, int64_t sT, int64_t sN, int T, int N, cons
 int ctc_blocked_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
                      int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank,
                      const float* gout, int64_t gout_stride, float* grad, const CtcScratch& sc, int vec,
-                     cudaStream_t st);
+                     cudaStream_t st, bool sparse_only = false);
+// dae_ctc_loss_grad: the class-dense part of the gradient as a dependent launch of the scan (ctc_blocked.cu, 5.)
+bool ctc_split_fits(const CtcScratch& sc, int N, int vec);
+int ctc_blocked_dense(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* in_len,
+                      const float* gout, int64_t gout_stride, float* grad, cudaStream_t st);
 
 }  // namespace dae

@@ -12,11 +12,12 @@ extern "C" int dae_abi_version(void) { return DAE_ABI_VERSION; }
 
 extern "C" int64_t dae_launch_count(void) { return dae::g_launches.load(std::memory_order_relaxed); }
 
-extern "C" void dae_ctc_configure(int blocked, int cluster, int pairs) {
+extern "C" void dae_ctc_configure(int blocked, int cluster, int pairs, int overlap) {
   dae::CtcConfig& c = dae::ctc_config();
   c.blocked.store(blocked < 0 ? -1 : (blocked ? 1 : 0));
   c.cluster.store(cluster);
   c.pairs.store(pairs);
+  c.overlap.store(overlap < 0 ? -1 : overlap);
 }
 
 extern "C" const char* dae_error_string(int code) {
@@ -41,8 +42,21 @@ CtcConfig& ctc_config() {
     cfg.blocked.store(env_int("DAE_CTC_BLOCKED", -1));
     cfg.cluster.store(env_int("DAE_CTC_CLUSTER", 0));
     cfg.pairs.store(env_int("DAE_CTC_PAIRS", 0));
+    cfg.overlap.store(env_int("DAE_CTC_OVERLAP", -1));
   });
   return cfg;
+}
+
+int sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
 }
 
 cudaError_t ensure_dyn_smem_impl(const void* kern, int bytes) {

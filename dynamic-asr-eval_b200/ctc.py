@@ -54,29 +54,31 @@ class _CTCFunction(torch.autograd.Function):
         nbytes = lib.dae_ctc_scratch_bytes(T, N, Lmax)
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         nll = torch.empty(N, dtype=torch.float32, device=dev)
+        ctx.blank = int(blank)
+        ctx.hint = None
+        if grad_scale_hint is not None and log_probs.requires_grad:
+            # the reference's `loss / (T*N); loss.backward()` (lcasr/lib.py:573-579): the upstream scale is known
+            # now, so loss and gradient are one library call (the dense part of the gradient runs under the
+            # lattice scan); backward() only checks the scale
+            ctx.hint = float(grad_scale_hint)
+            g = torch.full((1,), ctx.hint, dtype=torch.float32, device=dev)
+            grad = torch.empty((T, N, C), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev), prof.span("ctc_loss_grad", 2 * T * N * C * 4):
+                rc = lib.dae_ctc_loss_grad(lp.data_ptr(), lp.stride(0), lp.stride(1), T, N, C,
+                                           tg.data_ptr() if Lmax else None, tg.stride(0), Lmax,
+                                           in_len.data_ptr(), tg_len.data_ptr(), int(blank), nll.data_ptr(),
+                                           g.data_ptr(), 0, grad.data_ptr(), scratch.data_ptr(), nbytes,
+                                           _C.stream_ptr(dev))
+            _C.check(rc, "dae_ctc_loss_grad")
+            ctx.save_for_backward(grad)
+            ctx.shape = (T, N, C)
+            return nll
         with torch.cuda.device(dev), prof.span("ctc_lattice", T * N * C * 4):
             rc = lib.dae_ctc_lattice(lp.data_ptr(), lp.stride(0), lp.stride(1), T, N, C,
                                      tg.data_ptr() if Lmax else None, tg.stride(0), Lmax,
                                      in_len.data_ptr(), tg_len.data_ptr(), int(blank),
                                      nll.data_ptr(), scratch.data_ptr(), nbytes, _C.stream_ptr(dev))
         _C.check(rc, "dae_ctc_lattice")
-        ctx.blank = int(blank)
-        ctx.hint = None
-        if grad_scale_hint is not None and log_probs.requires_grad:
-            # the reference's `loss / (T*N); loss.backward()` (lcasr/lib.py:573-579): the upstream scale is known
-            # now, so the gradient launch follows the lattice launches directly; backward() only checks the scale
-            ctx.hint = float(grad_scale_hint)
-            g = torch.full((1,), ctx.hint, dtype=torch.float32, device=dev)
-            grad = torch.empty((T, N, C), dtype=torch.float32, device=dev)
-            with torch.cuda.device(dev), prof.span("ctc_grad", 2 * T * N * C * 4):
-                rc = lib.dae_ctc_grad(lp.data_ptr(), lp.stride(0), lp.stride(1), T, N, C,
-                                      tg.data_ptr() if Lmax else None, tg.stride(0), Lmax,
-                                      in_len.data_ptr(), tg_len.data_ptr(), int(blank), nll.data_ptr(), g.data_ptr(), 0,
-                                      grad.data_ptr(), scratch.data_ptr(), nbytes, _C.stream_ptr(dev))
-            _C.check(rc, "dae_ctc_grad")
-            ctx.save_for_backward(grad)
-            ctx.shape = (T, N, C)
-            return nll
         ctx.save_for_backward(lp, tg, in_len, tg_len, nll, scratch)
         return nll
 

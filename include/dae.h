@@ -169,13 +169,26 @@ int dae_ctc_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C,
  * kernel whose CTAs return after one load in the expected case. */
 int dae_ctc_rescale(float* grad, int T, int N, int C, const float* gout, int64_t gout_stride, float hint,
                     void* stream);
+/* dae_ctc_lattice followed by dae_ctc_grad as ONE call (same arguments, same results, scratch as for the pair):
+ * knowing that the gradient is wanted while the lattice is still running lets the library stream the class-dense
+ * part g*exp(lp) on the SMs the sequential scan leaves idle (few samples, many frames: the adapt step), so that
+ * only the few hundred label classes of every frame are left to do when the scan ends.  gout/grad as in
+ * dae_ctc_grad; nothing of `gout`, `lp` or `grad` may be produced by work queued on another stream. */
+int dae_ctc_loss_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C,
+                      const int64_t* tgt, int64_t tgt_stride, int Lmax,
+                      const int64_t* in_len, const int64_t* tgt_len, int blank,
+                      float* nll, const float* gout, int64_t gout_stride,
+                      float* grad, void* scratch, size_t scratch_bytes, void* stream);
 
 /* Debug/test switch for which CTC lattice implementation dae_ctc_lattice and dae_ctc_scratch_bytes pick
- * (process-wide; seeded once from the environment variables DAE_CTC_BLOCKED / DAE_CTC_CLUSTER / DAE_CTC_PAIRS):
+ * (process-wide; seeded once from the environment variables DAE_CTC_BLOCKED / DAE_CTC_CLUSTER / DAE_CTC_PAIRS /
+ * DAE_CTC_OVERLAP):
  *   blocked  -1 = by shape (default), 0 = always the per-frame chain, 1 = the time-blocked scan whenever it fits
  *   cluster  thread-block cluster size of the scan's region hand-over (1, 2, 4, 8; 0 = default 8; 1 = global memory only)
- *   pairs    state pairs per consumer thread of the per-frame chain (1, 2, 4; 0 = by label length) */
-void dae_ctc_configure(int blocked, int cluster, int pairs);
+ *   pairs    state pairs per consumer thread of the per-frame chain (1, 2, 4; 0 = by label length)
+ *   overlap  bit mask of what dae_ctc_loss_grad runs under the scan (-1 = everything, the default; 0 = nothing: the
+ *            call behaves as dae_ctc_lattice + dae_ctc_grad); bit 0 = the dense part of the gradient */
+void dae_ctc_configure(int blocked, int cluster, int pairs, int overlap);
 
 /* ------------------------------------------------------------------------------------
  * (f-1) overlap-average stitch of window posteriors, with a fused greedy argmax.

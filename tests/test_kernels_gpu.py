@@ -138,13 +138,15 @@ def test_specaug_plain_call_and_determinism(cuda):
 
 
 # ---------------------------------------------------------------- CTC
-@pytest.fixture(params=["chain", "blocked", "blocked_nocluster"])
+@pytest.fixture(params=["chain", "blocked", "blocked_nocluster", "blocked_serial"])
 def ctc_path(request):
     """Both lattice implementations behind dae_ctc_lattice: the per-frame chain (ctc.cu) and the time-blocked
-    scan (ctc_blocked.cu), the latter with hand-over through cluster shared memory (default) and through global
-    memory only; dae_ctc_configure forces the choice regardless of shape."""
+    scan (ctc_blocked.cu), the latter with hand-over through cluster shared memory (default), through global
+    memory only, and with dae_ctc_loss_grad's overlap of gradient and scan switched off;
+    dae_ctc_configure forces the choice regardless of shape."""
     import dae._C as C
-    C.ctc_configure(blocked=0 if request.param == "chain" else 1, cluster=1 if request.param == "blocked_nocluster" else 8)
+    C.ctc_configure(blocked=0 if request.param == "chain" else 1, cluster=1 if request.param == "blocked_nocluster" else 8,
+                    overlap=0 if request.param == "blocked_serial" else -1)
     yield request.param
     C.ctc_configure()
 
@@ -448,6 +450,45 @@ def test_ctc_rejects_out_of_range_labels(cuda):
     torch.cuda.synchronize()
     # The failing case is NOT run here: a device-side assert kills the CUDA context and is logged by the driver
     # as a GPU fault on this shared pool; the check itself is the torch._assert_async call in dae/ctc.py.
+
+
+@pytest.mark.parametrize("T,C,L,short", [(512, 256, 90, 0), (2048, 4096, 600, 0), (300, 64, 40, 37)])
+def test_ctc_loss_grad_one_call_matches_the_pair(cuda, T, C, L, short):
+    """dae_ctc_loss_grad (dense gradient streamed under the scan as a dependent launch, label classes after it) against
+    the same call with the overlap switched off (= dae_ctc_lattice + dae_ctc_grad) and against the fp64 oracle; a
+    reduction queued right behind it must see the finished gradient."""
+    import dae._C as C_
+    from dae.ctc import CTCLoss
+    g = torch.Generator().manual_seed(T + C)
+    tg = torch.randint(0, C - 1, (1, L), generator=g)
+    Ln = L
+    # teacher-like posteriors: frame t favours label floor(t*L/(T-short)) on two frames out of three, blank otherwise
+    t = torch.arange(T)
+    path = tg[0][(t * L // max(T - short, 1)).clamp(max=L - 1)]
+    path = torch.where(t % 3 == 2, torch.full_like(path, C - 1), path)
+    logits = torch.randn(T, 1, C, generator=g)
+    logits[t, 0, path] += 7.0
+    lp = logits.log_softmax(-1)
+    il, tl = torch.tensor([T - short], device=cuda), torch.tensor([Ln], device=cuda)
+    f = CTCLoss(blank=C - 1, reduction="sum")
+    out = {}
+    try:
+        for overlap in (0, -1):
+            C_.ctc_configure(blocked=1, overlap=overlap)
+            x = lp.to(cuda).requires_grad_()
+            loss = f.with_scale(x, tg.to(cuda), il, tl, grad_scale_hint=1.0 / T)
+            (loss / T).backward()
+            out[overlap] = (loss.detach().clone(), x.grad.clone(), x.grad.double().sum().item())
+    finally:
+        C_.ctc_configure()
+    assert torch.equal(out[0][0], out[-1][0])
+    torch.testing.assert_close(out[-1][1], out[0][1], rtol=1e-6, atol=1e-9)
+    assert torch.all(out[-1][1][T - short:] == 0)
+    nll, grad = ctc_oracle.ctc_loss_grad(lp.double().numpy(), tg.numpy(), [T - short], [Ln], C - 1, gout=1.0 / T)
+    assert abs(out[-1][0].item() - nll[0]) <= 1e-4 * abs(nll[0])
+    scale = np.abs(grad).max()
+    assert np.abs(out[-1][1].cpu().numpy() - grad).max() <= 1e-4 * scale
+    assert abs(out[-1][2] - out[-1][1].cpu().double().sum().item()) <= 1e-9 + 1e-9 * abs(out[-1][2])
 
 
 def test_ctc_gradient_formed_in_forward_with_scale_hint(cuda, ctc_path):

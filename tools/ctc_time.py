@@ -42,11 +42,39 @@ def fwd():
         f(x, tg, il, tl)
 
 
-for name, blocked in (("chain", 0), ("blocked", 1)):
+def queued(fn, reps=30):
+    """Device time of fn() when the host is ahead of the GPU (as inside the adapt step, behind the encoder's
+    kernels): a ~1 ms GEMM is queued first, then event / fn / event."""
+    big = torch.randn(8192, 8192, device="cuda")
+    ts = []
+    for _ in range(reps):
+        big @ big
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def lossgrad_only():
+    x.grad = None
+    f.with_scale(x, tg, il, tl, 1.0 / (T * N))
+
+
+for name, blocked, overlap in (("chain", 0, -1), ("blocked, serial (overlap=0)", 1, 0),
+                               ("blocked, dense gradient under the scan (1)", 1, 1)):
     if blocked and N > 8:
         continue
-    _C.ctc_configure(blocked=blocked)
+    if os.environ.get("DAE_ONLY_SERIAL") and overlap not in (0,):
+        continue
+    _C.ctc_configure(blocked=blocked, overlap=overlap)
     a, _ = tm.time(fb, 20)
     b, _ = tm.time(fwd, 20)
-    print(f"N={N} L={Lmax} {name}: loss+grad {a * 1e6:.1f} us, lattice only {b * 1e6:.1f} us", flush=True)
+    qm, qb = queued(lossgrad_only)
+    fm, fbst = queued(fwd)
+    print(f"N={N} L={Lmax} {name}: loss+grad {a * 1e6:.1f} us, lattice only {b * 1e6:.1f} us | host ahead: "
+          f"with_scale call {qm:.1f} us (best {qb:.1f}), lattice only {fm:.1f} us (best {fbst:.1f})", flush=True)
 _C.ctc_configure()

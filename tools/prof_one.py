@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--n", type=int, default=1)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--noflush", action="store_true")
+    ap.add_argument("--with-scale", action="store_true", help="ctc: loss and gradient as one call (the adapt step)")
     a = ap.parse_args()
     g = torch.Generator(device="cuda").manual_seed(0)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
@@ -46,7 +47,7 @@ def main():
             x.grad = None
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            loss = f(x, tg, il, tl)
+            loss = f.with_scale(x, tg, il, tl, 1.0 / T) if a.with_scale else f(x, tg, il, tl)
             e.record()
             scaled = loss / T
             s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

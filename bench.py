@@ -498,9 +498,11 @@ def run_dae(a, rank, world, local):
             traffic_warm = (tj.get("ctc_lattice+ctc_grad_warm_l2") or {}).get("bytes")
         roof = {"kernel": "ctc_lattice+ctc_grad (CTC loss+grad of one adapt step, T=2048 N=1 C=4096)", "bound": "hbm",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "traffic_note": "dram read+write of the three launches from one ncu --set full capture (caches flushed "
-                                "between kernels); with ncu --cache-control none the same launches move "
-                                f"{traffic_warm} bytes (bands/emissions stay in the 126 MB L2)",
+                "traffic_note": "dram read+write of the call's launches (bands, scan, dense gradient, label-class gradient) "
+                                "from one ncu --set full capture (caches flushed between kernels, so the gradient "
+                                "rows the last launch patches are fetched again); with ncu --cache-control none "
+                                f"the same launches move {traffic_warm} bytes (bands, emissions and the fresh "
+                                "gradient rows stay in the 126 MB L2)",
                 "algorithmic_bytes": by, "peak_source": peak_src, "avg_launch_us": t_pair * 1e3,
                 "note": "N=1: time-blocked lattice (transfer bands + 256-step boundary scan; the dense part of the gradient streams under the scan, the label classes follow it); the scan is a dependent chain (latency-bound); see DESIGN.md"}
     cpu = cpu_baseline_sample(a.frames) if world == 1 else None

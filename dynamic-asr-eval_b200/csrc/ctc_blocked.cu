@@ -927,8 +927,11 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
     __syncthreads();                             // also: lab, nxt, xbs, pads, label emissions are in smem
 #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
-      double ref = -CUDART_INF;
-      for (int w = 0; w < nw; ++w) ref = fmax(ref, red[dir * 32 + w]);
+      // maximum over the warps' candidates: one value per lane, five shuffle steps (max is exact: every warp
+      // arrives at the same double)
+      double ref = (lane < nw) ? red[dir * 32 + lane] : -CUDART_INF;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ref = fmax(ref, __shfl_xor_sync(0xffffffffu, ref, o));
       if (ref == -CUDART_INF) ref = 0.0;         // nothing alive (infeasible): any offset will do
       refd[dir] = ref;
 #pragma unroll

@@ -491,6 +491,47 @@ def test_ctc_loss_grad_one_call_matches_the_pair(cuda, T, C, L, short):
     assert abs(out[-1][2] - out[-1][1].cpu().double().sum().item()) <= 1e-9 + 1e-9 * abs(out[-1][2])
 
 
+@pytest.mark.parametrize("T,C", [(512, 64), (2048, 4096)])
+def test_ctc_one_call_is_repeatable_under_load(cuda, T, C):
+    """The one-call path runs three kernels at once (scan, dense gradient as its programmatic dependent, whatever the
+    caller queued before): the same call, repeated behind a GEMM / an elementwise kernel / nothing, must give the
+    same bits every time and torch's loss (tools/ctc_repeat.py is the longer version of this check)."""
+    import dae._C as C_
+    from dae.ctc import CTCLoss
+    g = torch.Generator().manual_seed(5)
+    L = T // 4
+    tg = torch.randint(0, C - 1, (1, L), generator=g)
+    t = torch.arange(T)
+    path = tg[0][(t * L // T).clamp(max=L - 1)]
+    path = torch.where(t % 3 == 2, torch.full_like(path, C - 1), path)
+    logits = torch.randn(T, 1, C, generator=g)
+    logits[t, 0, path] += 7.0
+    lp = logits.log_softmax(-1).to(cuda)
+    tgd, il, tl = tg.to(cuda), torch.tensor([T], device=cuda), torch.tensor([L], device=cuda)
+    ref = torch.nn.functional.ctc_loss(lp, tgd, il, tl, blank=C - 1, reduction="sum")
+    big, small = torch.randn(2048, 2048, device=cuda), torch.randn(1 << 20, device=cuda)
+    f = CTCLoss(blank=C - 1, reduction="sum", validate=False)
+    try:
+        for overlap in (0, -1):
+            C_.ctc_configure(blocked=1, overlap=overlap)
+            outs = []
+            for rep in range(9):
+                if rep % 3 == 1:
+                    big @ big
+                if rep % 3 == 2:
+                    small.mul_(1.0001)
+                x = lp.clone().requires_grad_()
+                loss = f.with_scale(x, tgd, il, tl, grad_scale_hint=1.0 / T)
+                (loss / T).backward()
+                outs.append((loss.detach().clone(), x.grad.clone()))
+            torch.cuda.synchronize()
+            for l_, g_ in outs[1:]:
+                assert torch.equal(l_, outs[0][0]) and torch.equal(g_, outs[0][1])
+            assert abs(outs[0][0].item() - ref.item()) <= 1e-4 * abs(ref.item())
+    finally:
+        C_.ctc_configure()
+
+
 def test_ctc_gradient_formed_in_forward_with_scale_hint(cuda, ctc_path):
     """CTCLoss.with_scale (the adapt loop's `loss / (T*N); backward()`): same loss, gradient bit-identical to the
     two-call path when the upstream gradient equals the hint, rescaled correctly when it does not."""

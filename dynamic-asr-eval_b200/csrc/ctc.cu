@@ -511,10 +511,13 @@ extern "C" int dae_ctc_loss_grad(const float* lp, int64_t sT, int64_t sN, int T,
                         stream, split);
   if (rc || N == 0 || T == 0) return rc;
   if (split) {
-    rc = ctc_blocked_dense(lp, sT, sN, T, N, C, in_len, gout, gout_stride, grad, (cudaStream_t)stream);
+    // bit 1: the label-class kernel is launched as a dependent of the dense kernel, loads its inputs while the scan
+    // runs and waits for the scan's CTAs itself; then the dense kernel need not outlive the scan
+    const bool early = (ctc_config().overlap.load(std::memory_order_relaxed) & 2) != 0;
+    rc = ctc_blocked_dense(lp, sT, sN, T, N, C, in_len, gout, gout_stride, grad, (cudaStream_t)stream, !early);
     if (rc) return rc;
     return ctc_blocked_grad(lp, sT, sN, T, N, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, gout, gout_stride, grad,
-                            sc, vec_g, (cudaStream_t)stream, true);
+                            sc, vec_g, (cudaStream_t)stream, true, early ? ctc_scan_ctas(sc, N) : 0);
   }
   return dae_ctc_grad(lp, sT, sN, T, N, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, nll, gout, gout_stride, grad,
                       scratch, scratch_bytes, stream);

@@ -39,6 +39,11 @@ __device__ __forceinline__ int2 ld_tagged(const int2* p) {
 __device__ __forceinline__ void st_tagged(int2* p, int2 v) {
   asm volatile("st.volatile.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
+__device__ __forceinline__ int ld_acquire_gpu_i32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void cp_async_f32(float* dst_smem, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
@@ -111,6 +116,7 @@ ctc_xfer_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, con
     const size_t n_thr = (size_t)gridDim.x * gridDim.y * gridDim.z * kXferTile;
     const size_t me = ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * kXferTile + tid;
     for (size_t w = me; w < n_words; w += n_thr) sc.halo[w] = make_int2(0, 0);
+    if (me < 64) sc.sync[me] = 0;
   }
   int Tn, L;
   clamp_lengths(in_len, tgt_len, n, T, Lmax, Tn, L);
@@ -245,6 +251,10 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
       const double ll = (L == 0) ? 0.0 : -(double)CUDART_INF_F;
       sc.ll2[dir * N + n] = ll;
       if (dir == 0) nll[n] = (float)(-ll);
+    }
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(sc.sync, 1);
     }
     return;
   }
@@ -559,6 +569,14 @@ ctc_boundary_kernel(int T, int Lmax, const int64_t* __restrict__ in_len, const i
     sc.ll2[dir * N + n] = ll2;
     if (dir == 0) nll[n] = (float)(-ll2 * kLn2d);
   }
+  // This CTA is done: count it for a gradient kernel that waits for the scan without a kernel boundary
+  // (ctc_block_grad_kernel, `wait_scan`).  The consumers meet at their own barrier (the helper warps have left),
+  // then one fence makes everything this CTA wrote - boundary vectors, frames, the likelihood - visible first.
+  asm volatile("bar.sync 1, %0;" ::"n"(kTpd * kRegion) : "memory");
+  if (tid == 0) {
+    __threadfence();
+    atomicAdd(sc.sync, 1);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ 3. block fill
@@ -787,7 +805,7 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
                       const int64_t* __restrict__ tgt, int64_t tgt_stride, int Lmax,
                       const int64_t* __restrict__ in_len, const int64_t* __restrict__ tgt_len, int blank,
                       const float* __restrict__ gout, int64_t gout_stride, float* __restrict__ grad, CtcScratch sc,
-                      BgSmem lay, int vec) {
+                      BgSmem lay, int vec, int wait_scan) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x, n = blockIdx.y, N = gridDim.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NTc = blockDim.x, nw = NTc >> 5;
@@ -867,7 +885,6 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
 
   // ---- 1a. labels, list links, emissions of the block's frames at every label state.  All global loads of the
   // prologue are issued before the dense stream starts, so their latency hides behind it.
-  const double ll2 = sc.ll2[n];
   int p2[P];
   bool lead_q[P];
   float xla[P][K];                               // emissions (log2) of this thread's label states, per frame
@@ -899,6 +916,19 @@ ctc_block_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
     for (int k = 0; k < K; ++k)
       if (p < Lp) gam[k * Lp + p] = xla[j][k];   // the beta chain reads them in reversed label order
   }
+  // `wait_scan` (SPARSE, launched as a programmatic dependent of the dense gradient kernel): the CTA has been
+  // resident and has loaded everything above while the scan was still running.  From here on it needs the scan's
+  // results, and its stores must follow the dense kernel's: wait for that grid, then for the scan's CTAs to have
+  // counted themselves (one poller per CTA; the scan never waits for anything, so this ends).
+  if (SPARSE && wait_scan > 0) {
+    cudaGridDependencySynchronize();
+    if (tid == 0) {
+      int spins = 0;
+      while (ld_acquire_gpu_i32(sc.sync) < wait_scan && ++spins < (1 << 22)) __nanosleep(128);
+    }
+    __syncthreads();
+  }
+  const double ll2 = sc.ll2[n];
   // ---- 1b. boundary vectors of both directions: every region carries its own frame; re-base on the largest value
   float2 v[2][P];
   double refd[2];
@@ -1143,11 +1173,27 @@ template <int P, int MAXT, int MINB, bool SPARSE>
 static int launch_block_grad(int NTc, cudaStream_t st, int N, const float* lp, int64_t sT, int64_t sN, int T, int C,
                              const int64_t* tgt, int64_t tgt_stride, int Lmax, const int64_t* in_len,
                              const int64_t* tgt_len, int blank, const float* gout, int64_t gout_stride, float* grad,
-                             const CtcScratch& sc, const BgSmem& lay, int vec) {
+                             const CtcScratch& sc, const BgSmem& lay, int vec, int wait_scan) {
   auto kern = ctc_block_grad_kernel<P, kBlkK, MAXT, MINB, SPARSE>;
   DAE_CUDA(ensure_dyn_smem(kern, lay.total));
+  if (SPARSE && wait_scan > 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sc.nblk, N);
+    cfg.blockDim = dim3(NTc);
+    cfg.dynamicSmemBytes = lay.total;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DAE_CUDA(cudaLaunchKernelEx(&cfg, kern, lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, gout,
+                                gout_stride, grad, sc, lay, vec, wait_scan));
+    DAE_LAUNCH_OK();
+    return 0;
+  }
   kern<<<dim3(sc.nblk, N), NTc, lay.total, st>>>(lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len, tgt_len, blank, gout,
-                                                 gout_stride, grad, sc, lay, vec);
+                                                 gout_stride, grad, sc, lay, vec, 0);
   DAE_LAUNCH_OK();
   return 0;
 }
@@ -1157,7 +1203,7 @@ static int launch_block_grad(int NTc, cudaStream_t st, int N, const float* lp, i
 int ctc_blocked_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
                      int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank,
                      const float* gout, int64_t gout_stride, float* grad, const CtcScratch& sc, int vec,
-                     cudaStream_t st, bool sparse_only) {
+                     cudaStream_t st, bool sparse_only, int wait_scan) {
   int P, NTc;
   lat_geometry(Lmax, P, NTc);
   const BgSmem lay = bg_smem_layout(sc.Lp, sc.Sp, kBlkK);
@@ -1170,9 +1216,9 @@ int ctc_blocked_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int 
   {                                                                                                                 \
     if (sparse_only)                                                                                                \
       return launch_block_grad<PP, MT, MB, true>(NTc, st, N, lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len,       \
-                                                 tgt_len, blank, gout, gout_stride, grad, sc, lay, vec);            \
+                                                 tgt_len, blank, gout, gout_stride, grad, sc, lay, vec, wait_scan); \
     return launch_block_grad<PP, MT, MB, false>(NTc, st, N, lp, sT, sN, T, C, tgt, tgt_stride, Lmax, in_len,        \
-                                                tgt_len, blank, gout, gout_stride, grad, sc, lay, vec);             \
+                                                tgt_len, blank, gout, gout_stride, grad, sc, lay, vec, 0);          \
   }
   constexpr int kMaxC = kLatThreads - 64;
   if (P <= 1 && NTc <= 640) DAE_BG(1, 640, 2);
@@ -1197,8 +1243,10 @@ constexpr int kScanCtasMax = 48;                  // the split path is taken whe
 __global__ void __launch_bounds__(kDenseThreads, 1)
 ctc_dense_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int T, int N, int C,
                       const int64_t* __restrict__ in_len, const float* __restrict__ gout, int64_t gout_stride,
-                      float* __restrict__ grad) {
+                      float* __restrict__ grad, int wait_for_scan) {
   constexpr int R = kDenseRows;
+  // the label-class gradient kernel behind this one may become resident (and load its inputs) right away
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int units_n = (T + R - 1) / R, C4 = C >> 2;
   for (int unit = blockIdx.x; unit < units_n * N; unit += gridDim.x) {
     const int n = unit / units_n, t0 = (unit - n * units_n) * R;
@@ -1223,8 +1271,11 @@ ctc_dense_grad_kernel(const float* __restrict__ lp, int64_t sT, int64_t sN, int 
     }
   }
   // completes only after the scan has: a later launch in the stream must not overtake the scan through this kernel
-  cudaGridDependencySynchronize();
+  // (not needed when the kernel behind it waits for the scan itself)
+  if (wait_for_scan) cudaGridDependencySynchronize();
 }
+
+int ctc_scan_ctas(const CtcScratch& sc, int N) { return 2 * sc.G * N; }
 
 bool ctc_split_fits(const CtcScratch& sc, int N, int vec) {
   if (!sc.xfer || !vec || sm_count() < 2 * kScanCtasMax) return false;
@@ -1235,7 +1286,7 @@ bool ctc_split_fits(const CtcScratch& sc, int N, int vec) {
 }
 
 int ctc_blocked_dense(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* in_len,
-                      const float* gout, int64_t gout_stride, float* grad, cudaStream_t st) {
+                      const float* gout, int64_t gout_stride, float* grad, cudaStream_t st, bool wait_for_scan) {
   DAE_CUDA(ensure_dyn_smem(ctc_dense_grad_kernel, kDenseSmemReserve));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(sm_count() - kScanCtasMax);
@@ -1247,7 +1298,8 @@ int ctc_blocked_dense(const float* lp, int64_t sT, int64_t sN, int T, int N, int
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DAE_CUDA(cudaLaunchKernelEx(&cfg, ctc_dense_grad_kernel, lp, sT, sN, T, N, C, in_len, gout, gout_stride, grad));
+  DAE_CUDA(cudaLaunchKernelEx(&cfg, ctc_dense_grad_kernel, lp, sT, sN, T, N, C, in_len, gout, gout_stride, grad,
+                              wait_for_scan ? 1 : 0));
   DAE_LAUNCH_OK();
   return 0;
 }

@@ -19,6 +19,7 @@ struct CtcScratch {           // carved out of the caller's scratch buffer
   double* off_a;              // [N][T]   alpha_t(s) = alpha[t][s] + off_a[t]   (log2 units)
   double* off_b;              // [N][T]   beta_t(s)  = beta_rev[t][S-1-s] + off_b[t]
   double* ll2;                // [4][N]   log2-likelihood from the alpha CTA, the beta CTA, then debug totals
+  int* sync;                  // [64]  time-blocked path: [0] scan CTAs that have finished (zeroed by the band kernel)
   int Sp, Lp;
   // ---- time-blocked path only (ctc_blocked.cu); null / 0 when the shape is not eligible
   float* xfer;                // [N][nblk][Sq][2K+1]  K-frame transfer bands, log2 units: xfer[b][s][d] = paths s -> s+d
@@ -42,7 +43,8 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 // Every consumer thread owns real or dummy pairs, so lattice rows are 2*NTc*P floats wide.
 // Path overrides (dae_ctc_configure): process-wide, read with relaxed atomics on every call; the environment
 // variables DAE_CTC_BLOCKED / DAE_CTC_CLUSTER / DAE_CTC_PAIRS / DAE_CTC_OVERLAP only seed them once, when the library
-// is first used.  overlap: bit 0 = dae_ctc_loss_grad streams the dense gradient under the scan; -1 = all on.
+// is first used.  overlap (dae_ctc_loss_grad): bit 0 = the dense gradient streams under the scan; bit 1 = the
+// label-class gradient kernel is resident and has loaded its inputs before the scan ends; -1 = all on.
 struct CtcConfig { std::atomic<int> blocked{-1}, cluster{0}, pairs{0}, overlap{-1}; };
 CtcConfig& ctc_config();
 
@@ -85,6 +87,7 @@ static inline size_t ctc_carve(CtcScratch& s, void* base, int T, int N, int Lmax
   s.off_a = (double*)(p + off); off += offs;
   s.off_b = (double*)(p + off); off += offs;
   s.ll2 = (double*)(p + off); off += align_up((size_t)4 * N * sizeof(double), 256);
+  s.sync = (int*)(p + off); off += 256;
   s.xfer = nullptr; s.bound = nullptr; s.boff = nullptr; s.halo = nullptr; s.emis = nullptr;
   s.nblk = 0; s.G = 0; s.Sq = 0;
   if (blocked_eligible(T, N, Lmax)) {
@@ -173,10 +176,11 @@ int ctc_blocked_fill(const float* lp, int64_t sT, int64_t sN, int T, int N, cons
 int ctc_blocked_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* tgt,
                      int64_t tgt_stride, int Lmax, const int64_t* in_len, const int64_t* tgt_len, int blank,
                      const float* gout, int64_t gout_stride, float* grad, const CtcScratch& sc, int vec,
-                     cudaStream_t st, bool sparse_only = false);
+                     cudaStream_t st, bool sparse_only = false, int scan_ctas_to_wait_for = 0);
 // dae_ctc_loss_grad: the class-dense part of the gradient as a dependent launch of the scan (ctc_blocked.cu, 5.)
 bool ctc_split_fits(const CtcScratch& sc, int N, int vec);
 int ctc_blocked_dense(const float* lp, int64_t sT, int64_t sN, int T, int N, int C, const int64_t* in_len,
-                      const float* gout, int64_t gout_stride, float* grad, cudaStream_t st);
+                      const float* gout, int64_t gout_stride, float* grad, cudaStream_t st, bool wait_for_scan);
+int ctc_scan_ctas(const CtcScratch& sc, int N);      // CTAs of the scan that count themselves in sc.sync[0]
 
 }  // namespace dae

@@ -187,7 +187,8 @@ int dae_ctc_loss_grad(const float* lp, int64_t sT, int64_t sN, int T, int N, int
  *   cluster  thread-block cluster size of the scan's region hand-over (1, 2, 4, 8; 0 = default 8; 1 = global memory only)
  *   pairs    state pairs per consumer thread of the per-frame chain (1, 2, 4; 0 = by label length)
  *   overlap  bit mask of what dae_ctc_loss_grad runs under the scan (-1 = everything, the default; 0 = nothing: the
- *            call behaves as dae_ctc_lattice + dae_ctc_grad); bit 0 = the dense part of the gradient */
+ *            call behaves as dae_ctc_lattice + dae_ctc_grad); bit 0 = the dense part of the gradient; bit 1 (with
+ *            bit 0) = the label-class gradient kernel is resident and has loaded its inputs before the scan ends */
 void dae_ctc_configure(int blocked, int cluster, int pairs, int overlap);
 
 /* ------------------------------------------------------------------------------------

@@ -473,7 +473,7 @@ def test_ctc_loss_grad_one_call_matches_the_pair(cuda, T, C, L, short):
     f = CTCLoss(blank=C - 1, reduction="sum")
     out = {}
     try:
-        for overlap in (0, -1):
+        for overlap in (0, 1, -1):
             C_.ctc_configure(blocked=1, overlap=overlap)
             x = lp.to(cuda).requires_grad_()
             loss = f.with_scale(x, tg.to(cuda), il, tl, grad_scale_hint=1.0 / T)
@@ -481,8 +481,9 @@ def test_ctc_loss_grad_one_call_matches_the_pair(cuda, T, C, L, short):
             out[overlap] = (loss.detach().clone(), x.grad.clone(), x.grad.double().sum().item())
     finally:
         C_.ctc_configure()
-    assert torch.equal(out[0][0], out[-1][0])
+    assert torch.equal(out[0][0], out[-1][0]) and torch.equal(out[0][0], out[1][0])
     torch.testing.assert_close(out[-1][1], out[0][1], rtol=1e-6, atol=1e-9)
+    assert torch.equal(out[-1][1], out[1][1])               # the early-resident kernel does the same arithmetic
     assert torch.all(out[-1][1][T - short:] == 0)
     nll, grad = ctc_oracle.ctc_loss_grad(lp.double().numpy(), tg.numpy(), [T - short], [Ln], C - 1, gout=1.0 / T)
     assert abs(out[-1][0].item() - nll[0]) <= 1e-4 * abs(nll[0])
@@ -512,7 +513,7 @@ def test_ctc_one_call_is_repeatable_under_load(cuda, T, C):
     big, small = torch.randn(2048, 2048, device=cuda), torch.randn(1 << 20, device=cuda)
     f = CTCLoss(blank=C - 1, reduction="sum", validate=False)
     try:
-        for overlap in (0, -1):
+        for overlap in (0, 1, -1):
             C_.ctc_configure(blocked=1, overlap=overlap)
             outs = []
             for rep in range(9):

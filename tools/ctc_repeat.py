@@ -33,7 +33,7 @@ for (T, C, N) in ((2048, 4096, 1), (2048, 4096, 2), (512, 64, 1), (40, 7, 2)):
     big = torch.randn(4096, 4096, device="cuda")
     small = torch.randn(1 << 20, device="cuda")
     f = CTCLoss(blank=C - 1, reduction="sum", validate=False)
-    for overlap in (0, 1):
+    for overlap in (0, 1, 3):
         _C.ctc_configure(blocked=1, overlap=overlap)
         for front in ("nothing", "elementwise", "gemm"):
             vals, grads = [], []

@@ -65,7 +65,8 @@ def lossgrad_only():
 
 
 for name, blocked, overlap in (("chain", 0, -1), ("blocked, serial (overlap=0)", 1, 0),
-                               ("blocked, dense gradient under the scan (1)", 1, 1)):
+                               ("blocked, dense gradient under the scan (1)", 1, 1),
+                               ("blocked, + label-class kernel resident early (3)", 1, 3)):
     if blocked and N > 8:
         continue
     if os.environ.get("DAE_ONLY_SERIAL") and overlap not in (0,):
